@@ -1,0 +1,183 @@
+/*
+ * gpusim.h - C ABI of the B200-native GPS L1 C/A baseband generator.
+ *
+ * This is the drop-in boundary for ONE path of gps-sdr-sim: the per-sample IQ
+ * synthesis loop and output quantise/pack of the reference
+ * (gpssim.c:2190-2264 and gpssim.c:2266-2288).  Everything above it - RINEX
+ * parsing, orbit propagation, computeRange/computeCodePhase, generateNavMsg,
+ * allocateChannel, the CLI - stays the reference's own host C code.  The host
+ * records, for every 0.1 s epoch and channel slot, the state the reference's
+ * sample loop would have started from (one row of gpusim_epoch_table) and
+ * hands batches of epochs to gpusim_generate_epochs*(), which returns exactly
+ * the bytes the reference's fwrite calls (gpssim.c:2276 / :2283 / :2287) would
+ * have produced for those epochs, in epoch order.
+ *
+ * The reference has no plugin / FFI interface for this path (the loop is inlined
+ * in main()), so every entry point below cites the reference lines it replaces.
+ * INTEGRATION.md shows the few lines a maintainer adds to gpssim.c to bind it.
+ *
+ * Plain C, plain pointers and sizes.  No CPU fallback exists: every compute
+ * entry point fails with GPUSIM_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef GPUSIM_H
+#define GPUSIM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPUSIM_ABI_VERSION 1
+
+/* gpssim.h:16  MAX_CHAN - channel slots per epoch row */
+#define GPUSIM_MAX_CHAN 16
+/* gpssim.h:36  CA_SEQ_LEN */
+#define GPUSIM_CA_SEQ_LEN 1023
+
+/* gpssim.h:77-79  SC01 / SC08 / SC16 */
+#define GPUSIM_SC01 1
+#define GPUSIM_SC08 8
+#define GPUSIM_SC16 16
+
+/* gpssim.h:4  which carrier-phase branch the host was compiled with */
+#define GPUSIM_CARRIER_INT 0   /* unsigned carr_phase + int carr_phasestep (gpssim.c:2202,:2252) */
+#define GPUSIM_CARRIER_FLOAT 1 /* double carr_phase, FLOAT_CARR_PHASE (gpssim.c:2200,:2245-2250) */
+
+/* status codes (0 = ok).  The reference's convention is "ERROR: ..." on stderr
+ * and exit(1) (e.g. gpssim.c:2076-2108); the host shim does that on non-zero. */
+#define GPUSIM_OK 0
+#define GPUSIM_ERR_ARG 1      /* bad argument / table violates a documented range */
+#define GPUSIM_ERR_CUDA 2     /* CUDA runtime error, or no usable device */
+#define GPUSIM_ERR_CAPACITY 3 /* batch larger than the context was created for */
+#define GPUSIM_ERR_SINK 4     /* the caller's sink returned non-zero */
+#define GPUSIM_ERR_UNSUPPORTED 5
+
+typedef struct gpusim_ctx gpusim_ctx;
+
+/* Scalars the reference fixes before its epoch loop. */
+typedef struct gpusim_config {
+    int32_t abi_version;       /* GPUSIM_ABI_VERSION */
+    int32_t device;            /* CUDA device ordinal */
+    int32_t samples_per_epoch; /* iq_buff_size = floor(fs/10)      gpssim.c:1877-1878 */
+    int32_t data_format;       /* GPUSIM_SC01/08/16 (-b)           gpssim.c:1797 */
+    int32_t carrier_mode;      /* GPUSIM_CARRIER_INT / _FLOAT      gpssim.h:4 */
+    int32_t max_batch_epochs;  /* capacity of one generate call */
+    double delt;               /* 1/(10*iq_buff_size)              gpssim.c:1881 */
+} gpusim_config;
+
+/*
+ * One batch of epochs, structure-of-arrays, host memory, row index
+ * e*GPUSIM_MAX_CHAN + slot.  A row is the value of the reference's per-channel
+ * state at the top of the sample loop (gpssim.c:2190) for that epoch, i.e.
+ * after the refresh at gpssim.c:2156-2188:
+ *
+ *   prn            chan[i].prn; 0 = slot not allocated (gpssim.c:2197 skips it)
+ *   f_code         chan[i].f_code                       (gpssim.c:1328)
+ *   code_phase     chan[i].code_phase, chips in [0,1023) (gpssim.c:1334)
+ *   icode          chan[i].icode, 0..19                  (gpssim.c:1342)
+ *   nav_bits       the next 32 navigation data bits starting at
+ *                  (chan[i].iword, chan[i].ibit), MSB first:
+ *                  bit 31 = (dwrd[iword]>>(29-ibit))&1   (gpssim.c:1345),
+ *                  bit 30 = the following bit, ... (an epoch consumes <= 7)
+ *   gain           gain[i]                               (gpssim.c:2186)
+ *   carr_phasestep chan[i].carr_phasestep                (gpssim.c:2176)   INT mode
+ *   carr_phase     chan[i].carr_phase at epoch start (the host advances it by
+ *                  samples_per_epoch*carr_phasestep mod 2^32 per epoch - the
+ *                  sample loop used to do that at gpssim.c:2252)           INT mode
+ *   f_carr         chan[i].f_carr                        (gpssim.c:1327)   FLOAT mode
+ *   carr_phase_f   chan[i].carr_phase (double) at epoch start              FLOAT mode
+ *
+ * Arrays of the other carrier mode may be NULL.  The library copies what it
+ * needs before returning; no pointer is retained.
+ */
+typedef struct gpusim_epoch_table {
+    int32_t n_epochs;
+    const int32_t *prn;
+    const double *f_code;
+    const double *code_phase;
+    const int32_t *icode;
+    const uint32_t *nav_bits;
+    const int32_t *gain;
+    const int32_t *carr_phasestep;
+    const uint32_t *carr_phase;
+    const double *f_carr;
+    const double *carr_phase_f;
+} gpusim_epoch_table;
+
+/* Ordered output sink: called with consecutive byte ranges of the output file
+ * (what fwrite(..., fp) received at gpssim.c:2276/:2283/:2287).  Non-zero aborts. */
+typedef int (*gpusim_sink_fn)(void *user, const void *bytes, size_t n_bytes);
+
+/* Device timing of the last generate call (CUDA events on the library's streams). */
+typedef struct gpusim_timing {
+    float chain_ms;      /* code-phase checkpoint kernel(s) */
+    float synth_ms;      /* generate + quantise + pack kernel(s) */
+    float total_ms;      /* first kernel start to last kernel end */
+    int32_t launches;    /* kernels launched by the call */
+    int32_t fast_path;   /* 1 = tuned kernel, 0 = generic kernel was needed */
+} gpusim_timing;
+
+int gpusim_abi_version(void);
+const char *gpusim_strerror(int status);
+/* text of the last failure on this context (or of gpusim_create when ctx==NULL) */
+const char *gpusim_last_error(const gpusim_ctx *ctx);
+
+int gpusim_create(const gpusim_config *cfg, gpusim_ctx **out_ctx);
+void gpusim_destroy(gpusim_ctx *ctx);
+
+/* bytes written per epoch: 4N (SC16), 2N (SC08), N/4 (SC01)   gpssim.c:2276,:2283,:2287 */
+size_t gpusim_epoch_bytes(const gpusim_ctx *ctx);
+
+/*
+ * Replaces gpssim.c:2190-2288 for table->n_epochs consecutive epochs.
+ * Host table in, host bytes out (out may be pageable); synchronous.
+ */
+int gpusim_generate_epochs(gpusim_ctx *ctx, const gpusim_epoch_table *table,
+                           void *out, size_t out_capacity);
+
+/*
+ * Same, but the bytes are delivered in order to `sink` from pinned staging
+ * buffers while later epochs are still being generated / copied
+ * (double-buffered cudaMemcpyAsync overlapped with the caller's fwrite).
+ */
+int gpusim_generate_epochs_to_sink(gpusim_ctx *ctx, const gpusim_epoch_table *table,
+                                   gpusim_sink_fn sink, void *user);
+
+/*
+ * Device-resident variant used for kernel timing and by callers that keep the
+ * samples on the GPU: upload once, then generate any epoch sub-range
+ * [first_epoch, first_epoch+n_epochs) of the uploaded table into device memory.
+ * `stream` is a cudaStream_t (NULL = the library's own stream); the call is
+ * asynchronous with respect to the host when a stream is given.
+ */
+int gpusim_upload_table(gpusim_ctx *ctx, const gpusim_epoch_table *table);
+int gpusim_generate_device(gpusim_ctx *ctx, int32_t first_epoch, int32_t n_epochs,
+                           void *out_device, size_t out_capacity, void *stream);
+
+int gpusim_get_timing(const gpusim_ctx *ctx, gpusim_timing *out);
+
+/* Tuning / test hooks (all optional).  key/value pairs documented in DESIGN.md:
+ *   "chunk"  samples per thread chunk (multiple of 32), 0 = auto
+ *   "force_generic" 1 = always use the generic exact kernel
+ *   "force_slow" 1 = always take the wrap-checking inner loop */
+int gpusim_set_option(gpusim_ctx *ctx, const char *key, int64_t value);
+
+/*
+ * Constant tables of the path, as the device uses them, for parity tests:
+ *   sin512/cos512  -> sinTable512 / cosTable512  (gpssim.c:15-83), 512 ints each
+ *   ca             -> codegen(ca, prn)           (gpssim.c:132-171), 1023 ints in {0,1}
+ * Host-side, no GPU needed.
+ */
+void gpusim_carrier_lut(int32_t *sin512, int32_t *cos512);
+int gpusim_ca_code(int32_t prn, int32_t *ca1023);
+
+/* Pack the 32 data bits starting at (iword, ibit) of a dwrd[60] word buffer
+ * (gpssim.h:175, unsigned long on the host) into the nav_bits row format. */
+uint32_t gpusim_pack_nav_bits(const unsigned long *dwrd, int32_t n_dwrd, int32_t iword, int32_t ibit);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPUSIM_H */

@@ -1,0 +1,493 @@
+// gpusim_api.cu - the C ABI of include/gpusim.h: context, table upload, batching,
+// double-buffered device->host streaming.  The kernels are in gpusim_kernels.cu.
+//
+// There is deliberately no CPU path: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gpusim.h"
+#include "gpusim_kernels.h"
+#include "gpusim_tables.h"
+
+using namespace gpusim;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr size_t kStageBytes = 64u << 20;      // one pinned staging buffer / sub-batch of output
+constexpr size_t kCheckpointBudget = 1u << 30; // device bytes for K1 checkpoints
+
+} // namespace
+
+struct gpusim_ctx {
+    gpusim_config cfg{};
+    size_t epoch_bytes = 0;
+    std::string err;
+
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_t2 = nullptr;
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+
+    // constant tables
+    int32_t *d_lut = nullptr;
+    int16_t *d_sin16 = nullptr, *d_cos16 = nullptr;
+    uint32_t *d_negw = nullptr;
+
+    // uploaded table (capacity cfg.max_batch_epochs)
+    DevRow *d_rows = nullptr, *h_rows = nullptr;
+    uint8_t *d_nch = nullptr, *h_nch = nullptr;
+    double *d_x0 = nullptr, *h_x0 = nullptr;
+    int n_uploaded = 0;
+    bool needs_generic = false;
+    double d_max = 0.0;
+
+    // checkpoints, sized for min_chunk
+    double *d_ck_x = nullptr;
+    uint16_t *d_ck_w = nullptr;
+    int min_chunk = 128;
+
+    // output
+    uint8_t *d_out = nullptr; // lazily: max_batch_epochs * epoch_bytes
+    uint8_t *h_stage[2] = {nullptr, nullptr};
+
+    // options
+    int opt_chunk = 0, opt_force_generic = 0, opt_force_slow = 0, opt_chain_replay = 0;
+
+    gpusim_timing timing{};
+};
+
+namespace {
+
+int fail(gpusim_ctx *ctx, int status, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx)
+        ctx->err = buf;
+    else
+        g_create_error = buf;
+    return status;
+}
+
+#define GS_CUDA(ctx, call)                                                                     \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(ctx, GPUSIM_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+int kc_for(int n_samples, int chunk) { return (n_samples + chunk - 1) / chunk; }
+
+// samples per thread chunk: as large as still gives ~2 waves of 512-thread blocks on 148 SMs
+int pick_chunk(const gpusim_ctx *ctx, int n_epochs)
+{
+    if (ctx->opt_chunk > 0)
+        return std::max(ctx->min_chunk, (ctx->opt_chunk + 31) / 32 * 32);
+    const long long want = 2LL * 148 * synth_threads();
+    int chunk = 1024;
+    while (chunk > ctx->min_chunk && (long long)n_epochs * kc_for(ctx->cfg.samples_per_epoch, chunk) < want)
+        chunk /= 2;
+    return std::max(chunk, ctx->min_chunk);
+}
+
+int ensure_out(gpusim_ctx *ctx)
+{
+    if (ctx->d_out == nullptr)
+        GS_CUDA(ctx, cudaMalloc(&ctx->d_out, std::max<size_t>(16, (size_t)ctx->cfg.max_batch_epochs * ctx->epoch_bytes)));
+    return GPUSIM_OK;
+}
+
+int ensure_stage(gpusim_ctx *ctx)
+{
+    for (int i = 0; i < 2; i++)
+        if (ctx->h_stage[i] == nullptr)
+            GS_CUDA(ctx, cudaMallocHost(&ctx->h_stage[i], std::max(kStageBytes, ctx->epoch_bytes)));
+    return GPUSIM_OK;
+}
+
+// launch K1 + K2 for uploaded epochs [first, first+n) into out_dev on `stream`
+int launch_range(gpusim_ctx *ctx, int first, int n, uint8_t *out_dev, cudaStream_t stream, bool timed)
+{
+    if (n <= 0)
+        return GPUSIM_OK;
+    DeviceJob job{};
+    job.rows = ctx->d_rows + (size_t)first * kMaxChan;
+    job.nch = ctx->d_nch + first;
+    job.x0 = ctx->d_x0 + (size_t)first * kMaxChan;
+    job.ck_x = ctx->d_ck_x;
+    job.ck_w = ctx->d_ck_w;
+    job.lut = ctx->d_lut;
+    job.sin16 = ctx->d_sin16;
+    job.cos16 = ctx->d_cos16;
+    job.negw = ctx->d_negw;
+    job.out = out_dev;
+    job.n_epochs = n;
+    job.n_samples = ctx->cfg.samples_per_epoch;
+    job.chunk = pick_chunk(ctx, n);
+    job.kc = kc_for(job.n_samples, job.chunk);
+    job.fmt = ctx->cfg.data_format;
+    job.epoch_bytes = (int32_t)ctx->epoch_bytes;
+    job.max_active = 1;
+    for (int e = first; e < first + n; e++)
+        job.max_active = std::max<int>(job.max_active, ctx->h_nch[e]);
+    job.force_wrap_path = ctx->opt_force_slow;
+
+    SynthKernel which = SynthKernel::Tuned32;
+    if (ctx->opt_force_generic || ctx->needs_generic || (job.n_samples % 32) != 0 || ctx->d_max >= 2.0)
+        which = SynthKernel::Generic;
+    else if (ctx->d_max > 0.9999)
+        which = SynthKernel::Tuned16;
+
+    if (timed)
+        GS_CUDA(ctx, cudaEventRecord(ctx->ev_t0, stream));
+    GS_CUDA(ctx, launch_chain(job, ctx->opt_chain_replay ? ChainAlgo::Replay : ChainAlgo::Jump, stream));
+    if (timed)
+        GS_CUDA(ctx, cudaEventRecord(ctx->ev_t1, stream));
+    GS_CUDA(ctx, launch_synth(job, which, stream));
+    if (timed)
+        GS_CUDA(ctx, cudaEventRecord(ctx->ev_t2, stream));
+    ctx->timing.launches += 2;
+    ctx->timing.fast_path = (which != SynthKernel::Generic) ? 1 : 0;
+    return GPUSIM_OK;
+}
+
+int collect_timing(gpusim_ctx *ctx)
+{
+    float a = 0.f, b = 0.f;
+    GS_CUDA(ctx, cudaEventSynchronize(ctx->ev_t2));
+    GS_CUDA(ctx, cudaEventElapsedTime(&a, ctx->ev_t0, ctx->ev_t1));
+    GS_CUDA(ctx, cudaEventElapsedTime(&b, ctx->ev_t1, ctx->ev_t2));
+    ctx->timing.chain_ms += a;
+    ctx->timing.synth_ms += b;
+    ctx->timing.total_ms += a + b;
+    return GPUSIM_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int gpusim_abi_version(void) { return GPUSIM_ABI_VERSION; }
+
+const char *gpusim_strerror(int status)
+{
+    switch (status) {
+    case GPUSIM_OK: return "ok";
+    case GPUSIM_ERR_ARG: return "invalid argument or table value out of range";
+    case GPUSIM_ERR_CUDA: return "CUDA error / no usable device";
+    case GPUSIM_ERR_CAPACITY: return "batch exceeds the context's capacity";
+    case GPUSIM_ERR_SINK: return "output sink failed";
+    case GPUSIM_ERR_UNSUPPORTED: return "not supported by this build";
+    default: return "unknown status";
+    }
+}
+
+const char *gpusim_last_error(const gpusim_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+size_t gpusim_epoch_bytes(const gpusim_ctx *ctx) { return ctx ? ctx->epoch_bytes : 0; }
+
+void gpusim_destroy(gpusim_ctx *ctx)
+{
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->cfg.device);
+    if (ctx->s_compute) cudaStreamSynchronize(ctx->s_compute);
+    if (ctx->s_copy) cudaStreamSynchronize(ctx->s_copy);
+    cudaFree(ctx->d_lut); cudaFree(ctx->d_sin16); cudaFree(ctx->d_cos16); cudaFree(ctx->d_negw);
+    cudaFree(ctx->d_rows); cudaFree(ctx->d_nch); cudaFree(ctx->d_x0);
+    cudaFree(ctx->d_ck_x); cudaFree(ctx->d_ck_w); cudaFree(ctx->d_out);
+    cudaFreeHost(ctx->h_rows); cudaFreeHost(ctx->h_nch); cudaFreeHost(ctx->h_x0);
+    cudaFreeHost(ctx->h_stage[0]); cudaFreeHost(ctx->h_stage[1]);
+    for (cudaEvent_t ev : {ctx->ev_t0, ctx->ev_t1, ctx->ev_t2, ctx->ev_done[0], ctx->ev_done[1],
+                           ctx->ev_copied[0], ctx->ev_copied[1]})
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
+    if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
+    delete ctx;
+}
+
+int gpusim_create(const gpusim_config *cfg, gpusim_ctx **out_ctx)
+{
+    if (!cfg || !out_ctx)
+        return fail(nullptr, GPUSIM_ERR_ARG, "gpusim_create: null argument");
+    *out_ctx = nullptr;
+    if (cfg->abi_version != GPUSIM_ABI_VERSION)
+        return fail(nullptr, GPUSIM_ERR_ARG, "ABI version mismatch: host %d, library %d", cfg->abi_version, GPUSIM_ABI_VERSION);
+    if (cfg->samples_per_epoch < 1 || cfg->max_batch_epochs < 1 || !(cfg->delt > 0.0))
+        return fail(nullptr, GPUSIM_ERR_ARG, "samples_per_epoch, max_batch_epochs and delt must be positive");
+    if (cfg->data_format != GPUSIM_SC01 && cfg->data_format != GPUSIM_SC08 && cfg->data_format != GPUSIM_SC16)
+        return fail(nullptr, GPUSIM_ERR_ARG, "data_format must be 1, 8 or 16");
+    if (cfg->carrier_mode == GPUSIM_CARRIER_FLOAT)
+        return fail(nullptr, GPUSIM_ERR_UNSUPPORTED,
+                    "FLOAT_CARR_PHASE hosts are not supported yet: build the host with gpssim.h:4 disabled");
+    if (cfg->carrier_mode != GPUSIM_CARRIER_INT)
+        return fail(nullptr, GPUSIM_ERR_ARG, "unknown carrier_mode");
+
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(nullptr, GPUSIM_ERR_CUDA, "no CUDA device: %s (this library has no CPU path)",
+                    ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0");
+    if (cfg->device < 0 || cfg->device >= ndev)
+        return fail(nullptr, GPUSIM_ERR_ARG, "device %d out of range (0..%d)", cfg->device, ndev - 1);
+
+    gpusim_ctx *ctx = new gpusim_ctx();
+    ctx->cfg = *cfg;
+    const int N = cfg->samples_per_epoch;
+    ctx->epoch_bytes = cfg->data_format == GPUSIM_SC01 ? (size_t)(N / 4) : cfg->data_format == GPUSIM_SC08 ? (size_t)2 * N : (size_t)4 * N;
+
+#define GS_CREATE(call)                                                                            \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            fail(nullptr, GPUSIM_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));         \
+            gpusim_destroy(ctx);                                                                   \
+            return GPUSIM_ERR_CUDA;                                                                \
+        }                                                                                          \
+    } while (0)
+
+    GS_CREATE(cudaSetDevice(cfg->device));
+    GS_CREATE(cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));
+    GS_CREATE(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
+    GS_CREATE(cudaEventCreate(&ctx->ev_t0));
+    GS_CREATE(cudaEventCreate(&ctx->ev_t1));
+    GS_CREATE(cudaEventCreate(&ctx->ev_t2));
+    for (int i = 0; i < 2; i++) {
+        GS_CREATE(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+        GS_CREATE(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+    }
+
+    // constant tables
+    {
+        int32_t s[512], c[512], lut[512];
+        int16_t s16[512], c16[512];
+        carrier_lut(s, c);
+        for (int i = 0; i < 512; i++) {
+            lut[i] = lut_word(c[i], s[i]);
+            s16[i] = (int16_t)s[i];
+            c16[i] = (int16_t)c[i];
+        }
+        std::vector<uint32_t> negw((size_t)kCaPrns * kCaWords, 0xffffffffu);
+        for (int prn = 1; prn <= 32; prn++) {
+            uint32_t w[kCaWords];
+            ca_words(prn, w);
+            for (int i = 0; i < kCaWords; i++)
+                negw[(size_t)prn * kCaWords + i] = ~w[i]; // bit set = chip 0 = codeCA -1 (gpssim.c:2241)
+        }
+        GS_CREATE(cudaMalloc(&ctx->d_lut, sizeof(lut)));
+        GS_CREATE(cudaMalloc(&ctx->d_sin16, sizeof(s16)));
+        GS_CREATE(cudaMalloc(&ctx->d_cos16, sizeof(c16)));
+        GS_CREATE(cudaMalloc(&ctx->d_negw, negw.size() * sizeof(uint32_t)));
+        GS_CREATE(cudaMemcpy(ctx->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+        GS_CREATE(cudaMemcpy(ctx->d_sin16, s16, sizeof(s16), cudaMemcpyHostToDevice));
+        GS_CREATE(cudaMemcpy(ctx->d_cos16, c16, sizeof(c16), cudaMemcpyHostToDevice));
+        GS_CREATE(cudaMemcpy(ctx->d_negw, negw.data(), negw.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+
+    const size_t rows = (size_t)cfg->max_batch_epochs * kMaxChan;
+    GS_CREATE(cudaMalloc(&ctx->d_rows, rows * sizeof(DevRow)));
+    GS_CREATE(cudaMalloc(&ctx->d_nch, (size_t)cfg->max_batch_epochs));
+    GS_CREATE(cudaMalloc(&ctx->d_x0, rows * sizeof(double)));
+    GS_CREATE(cudaMallocHost(&ctx->h_rows, rows * sizeof(DevRow)));
+    GS_CREATE(cudaMallocHost(&ctx->h_nch, (size_t)cfg->max_batch_epochs));
+    GS_CREATE(cudaMallocHost(&ctx->h_x0, rows * sizeof(double)));
+
+    // checkpoints: 10 bytes per (row, chunk); raise the minimum chunk until they fit the budget
+    ctx->min_chunk = 128;
+    while (rows * (size_t)kc_for(N, ctx->min_chunk) * 10 > kCheckpointBudget && ctx->min_chunk < (1 << 20))
+        ctx->min_chunk *= 2;
+    const size_t cks = rows * (size_t)kc_for(N, ctx->min_chunk);
+    GS_CREATE(cudaMalloc(&ctx->d_ck_x, cks * sizeof(double)));
+    GS_CREATE(cudaMalloc(&ctx->d_ck_w, cks * sizeof(uint16_t)));
+#undef GS_CREATE
+
+    *out_ctx = ctx;
+    return GPUSIM_OK;
+}
+
+int gpusim_set_option(gpusim_ctx *ctx, const char *key, int64_t value)
+{
+    if (!ctx || !key)
+        return GPUSIM_ERR_ARG;
+    if (!strcmp(key, "chunk")) ctx->opt_chunk = (int)value;
+    else if (!strcmp(key, "force_generic")) ctx->opt_force_generic = (int)value;
+    else if (!strcmp(key, "force_slow")) ctx->opt_force_slow = (int)value;
+    else if (!strcmp(key, "chain_replay")) ctx->opt_chain_replay = (int)value;
+    else return fail(ctx, GPUSIM_ERR_ARG, "unknown option '%s'", key);
+    return GPUSIM_OK;
+}
+
+int gpusim_upload_table(gpusim_ctx *ctx, const gpusim_epoch_table *t)
+{
+    if (!ctx || !t)
+        return GPUSIM_ERR_ARG;
+    if (t->n_epochs < 0 || t->n_epochs > ctx->cfg.max_batch_epochs)
+        return fail(ctx, GPUSIM_ERR_CAPACITY, "table has %d epochs, context capacity is %d", t->n_epochs, ctx->cfg.max_batch_epochs);
+    if (!t->prn || !t->f_code || !t->code_phase || !t->icode || !t->nav_bits || !t->gain || !t->carr_phasestep || !t->carr_phase)
+        return fail(ctx, GPUSIM_ERR_ARG, "integer-carrier tables need prn, f_code, code_phase, icode, nav_bits, gain, carr_phasestep, carr_phase");
+    GS_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    // the previous upload may still be read by kernels in flight
+    GS_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
+
+    const double delt = ctx->cfg.delt;
+    ctx->needs_generic = false;
+    ctx->d_max = 0.0;
+    for (int e = 0; e < t->n_epochs; e++) {
+        int nc = 0;
+        for (int i = 0; i < kMaxChan; i++) {
+            const size_t r = (size_t)e * kMaxChan + i;
+            if (t->prn[r] <= 0) // gpssim.c:2197: slot skipped
+                continue;
+            if (t->prn[r] > 32)
+                return fail(ctx, GPUSIM_ERR_ARG, "epoch %d slot %d: prn %d (1..32 have C/A codes, gpssim.c:145)", e, i, t->prn[r]);
+            const double x0 = t->code_phase[r];
+            const volatile double d = t->f_code[r] * delt; // the reference's rounded product, gpssim.c:2212
+            if (!(x0 >= 0.0 && x0 < (double)kCaLen) || !(d > 0.0 && d < (double)kCaLen) || t->icode[r] < 0 || t->icode[r] > 19)
+                return fail(ctx, GPUSIM_ERR_ARG, "epoch %d slot %d: code_phase %.17g, f_code*delt %.17g or icode %d outside the reference's invariants", e, i, x0, (double)d, t->icode[r]);
+            DevRow &o = ctx->h_rows[(size_t)e * kMaxChan + nc];
+            o.d = d;
+            o.ph0 = t->carr_phase[r];
+            o.step = t->carr_phasestep[r];
+            o.gain = t->gain[r];
+            o.nav_bits = t->nav_bits[r];
+            o.prn = (uint16_t)t->prn[r];
+            o.icode0 = (uint16_t)t->icode[r];
+            o.flags = 0;
+            if (o.gain < 0 || o.gain > kTunedMaxGain) {
+                o.flags |= kRowNeedsGeneric;
+                ctx->needs_generic = true;
+            }
+            ctx->d_max = std::max(ctx->d_max, (double)d);
+            ctx->h_x0[(size_t)e * kMaxChan + nc] = x0;
+            nc++;
+        }
+        for (int k = nc; k < kMaxChan; k++) {
+            memset(&ctx->h_rows[(size_t)e * kMaxChan + k], 0, sizeof(DevRow));
+            ctx->h_x0[(size_t)e * kMaxChan + k] = 0.0;
+        }
+        ctx->h_nch[e] = (uint8_t)nc;
+    }
+    const size_t rows = (size_t)t->n_epochs * kMaxChan;
+    if (rows) {
+        GS_CUDA(ctx, cudaMemcpyAsync(ctx->d_rows, ctx->h_rows, rows * sizeof(DevRow), cudaMemcpyHostToDevice, ctx->s_compute));
+        GS_CUDA(ctx, cudaMemcpyAsync(ctx->d_x0, ctx->h_x0, rows * sizeof(double), cudaMemcpyHostToDevice, ctx->s_compute));
+        GS_CUDA(ctx, cudaMemcpyAsync(ctx->d_nch, ctx->h_nch, (size_t)t->n_epochs, cudaMemcpyHostToDevice, ctx->s_compute));
+        GS_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
+    }
+    ctx->n_uploaded = t->n_epochs;
+    return GPUSIM_OK;
+}
+
+int gpusim_generate_device(gpusim_ctx *ctx, int32_t first, int32_t n, void *out_device, size_t cap, void *stream)
+{
+    if (!ctx)
+        return GPUSIM_ERR_ARG;
+    if (first < 0 || n < 0 || first + n > ctx->n_uploaded)
+        return fail(ctx, GPUSIM_ERR_ARG, "epoch range [%d,%d) outside the uploaded table (%d epochs)", first, first + n, ctx->n_uploaded);
+    if ((size_t)n * ctx->epoch_bytes > cap)
+        return fail(ctx, GPUSIM_ERR_CAPACITY, "output needs %zu bytes, capacity is %zu", (size_t)n * ctx->epoch_bytes, cap);
+    if (!out_device || ((uintptr_t)out_device & 15))
+        return fail(ctx, GPUSIM_ERR_ARG, "out_device must be a 16-byte aligned device pointer");
+    GS_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->s_compute;
+    ctx->timing = gpusim_timing{};
+    int rc = launch_range(ctx, first, n, (uint8_t *)out_device, s, true);
+    if (rc != GPUSIM_OK)
+        return rc;
+    if (!stream)
+        GS_CUDA(ctx, cudaStreamSynchronize(s));
+    return GPUSIM_OK;
+}
+
+int gpusim_get_timing(const gpusim_ctx *cctx, gpusim_timing *out)
+{
+    gpusim_ctx *ctx = const_cast<gpusim_ctx *>(cctx);
+    if (!ctx || !out)
+        return GPUSIM_ERR_ARG;
+    if (ctx->timing.launches > 0 && ctx->timing.total_ms == 0.f) {
+        int rc = collect_timing(ctx);
+        if (rc != GPUSIM_OK)
+            return rc;
+    }
+    *out = ctx->timing;
+    return GPUSIM_OK;
+}
+
+// common driver of the two host-output entry points: sub-batches of <= kStageBytes are generated
+// on s_compute and copied back on s_copy while the next sub-batch is being generated
+static int generate_to_host(gpusim_ctx *ctx, const gpusim_epoch_table *t, uint8_t *out, gpusim_sink_fn sink, void *user)
+{
+    int rc = gpusim_upload_table(ctx, t);
+    if (rc != GPUSIM_OK)
+        return rc;
+    if ((rc = ensure_out(ctx)) != GPUSIM_OK)
+        return rc;
+    if (sink && (rc = ensure_stage(ctx)) != GPUSIM_OK)
+        return rc;
+    ctx->timing = gpusim_timing{};
+    const int n = t->n_epochs;
+    const size_t eb = ctx->epoch_bytes;
+    if (n == 0 || eb == 0)
+        return GPUSIM_OK;
+    const int sub = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, kStageBytes / eb));
+
+    int pending = -1; // sub-batch whose copy has been issued but not yet delivered
+    int pending_first = 0, pending_n = 0;
+    int b = 0;
+    for (int first = 0; first < n; first += sub, b++) {
+        const int cnt = std::min(sub, n - first);
+        uint8_t *dst_dev = ctx->d_out + (size_t)first * eb;
+        if ((rc = launch_range(ctx, first, cnt, dst_dev, ctx->s_compute, true)) != GPUSIM_OK)
+            return rc;
+        GS_CUDA(ctx, cudaEventRecord(ctx->ev_done[b & 1], ctx->s_compute));
+        GS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_copy, ctx->ev_done[b & 1], 0));
+        uint8_t *dst_host = sink ? ctx->h_stage[b & 1] : out + (size_t)first * eb;
+        GS_CUDA(ctx, cudaMemcpyAsync(dst_host, dst_dev, (size_t)cnt * eb, cudaMemcpyDeviceToHost, ctx->s_copy));
+        GS_CUDA(ctx, cudaEventRecord(ctx->ev_copied[b & 1], ctx->s_copy));
+        // deliver the previous sub-batch while this one is generated and copied
+        if (pending >= 0 && sink) {
+            GS_CUDA(ctx, cudaEventSynchronize(ctx->ev_copied[pending & 1]));
+            if (sink(user, ctx->h_stage[pending & 1], (size_t)pending_n * eb) != 0)
+                return fail(ctx, GPUSIM_ERR_SINK, "sink failed at epoch %d", pending_first);
+        }
+        if ((rc = collect_timing(ctx)) != GPUSIM_OK) // also orders reuse of the timing events
+            return rc;
+        pending = b;
+        pending_first = first;
+        pending_n = cnt;
+    }
+    GS_CUDA(ctx, cudaStreamSynchronize(ctx->s_copy));
+    if (pending >= 0 && sink)
+        if (sink(user, ctx->h_stage[pending & 1], (size_t)pending_n * eb) != 0)
+            return fail(ctx, GPUSIM_ERR_SINK, "sink failed at epoch %d", pending_first);
+    return GPUSIM_OK;
+}
+
+int gpusim_generate_epochs(gpusim_ctx *ctx, const gpusim_epoch_table *t, void *out, size_t cap)
+{
+    if (!ctx || !t || !out)
+        return GPUSIM_ERR_ARG;
+    if ((size_t)t->n_epochs * ctx->epoch_bytes > cap)
+        return fail(ctx, GPUSIM_ERR_CAPACITY, "output needs %zu bytes, capacity is %zu", (size_t)t->n_epochs * ctx->epoch_bytes, cap);
+    return generate_to_host(ctx, t, (uint8_t *)out, nullptr, nullptr);
+}
+
+int gpusim_generate_epochs_to_sink(gpusim_ctx *ctx, const gpusim_epoch_table *t, gpusim_sink_fn sink, void *user)
+{
+    if (!ctx || !t || !sink)
+        return GPUSIM_ERR_ARG;
+    return generate_to_host(ctx, t, nullptr, sink, user);
+}
+
+} // extern "C"

@@ -1,0 +1,261 @@
+// gpusim_kernels.cu - hand-written sm_100a kernels of the sample-synthesis path.
+//
+//   k1_chain    one thread per (epoch, channel): exact code-phase checkpoints
+//               (replaces the loop-carried dependency of gpssim.c:2212-2218)
+//   k2_synth    one thread per chunk of consecutive samples: carrier table x C/A chip x
+//               data bit x gain summed over channels, rounded and packed
+//               (replaces gpssim.c:2192-2263 and the formatter at :2266-2288)
+//   k2_generic  same result, no range assumptions, scalar stores
+//
+// The arithmetic lives in gpusim_core.h; this file is the mapping onto threads, shared
+// memory and global memory.  Not a contraction: no tensor cores.  The bound is
+// instruction issue (INT / FP64 / LDS per sample and channel) below an HBM-write roof.
+#include <cuda_runtime.h>
+
+#include "gpusim_kernels.h"
+
+namespace gpusim {
+
+// ------------------------------------------------------------------------------------
+// K1
+// ------------------------------------------------------------------------------------
+template <bool kReplay>
+__global__ void __launch_bounds__(128) k1_chain(DeviceJob job)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = idx / kMaxChan;
+    const int k = idx % kMaxChan;
+    if (e >= job.n_epochs || k >= job.nch[e])
+        return;
+    const size_t row = (size_t)e * kMaxChan + k;
+    const double d = job.rows[row].d;
+    const double x0 = job.x0[row];
+    double *cx = job.ck_x + row * job.kc;
+    uint16_t *cw = job.ck_w + row * job.kc;
+    auto emit = [&](int j, double x, int wraps) {
+        cx[j] = x;
+        cw[j] = (uint16_t)wraps;
+    };
+    if (kReplay)
+        code_chain_replay(x0, d, job.n_samples, job.chunk, emit);
+    else
+        code_chain(x0, d, job.n_samples, job.chunk, emit);
+}
+
+cudaError_t launch_chain(const DeviceJob &job, ChainAlgo algo, cudaStream_t stream)
+{
+    const int threads = 128;
+    const int total = job.n_epochs * kMaxChan;
+    const int blocks = (total + threads - 1) / threads;
+    if (blocks == 0)
+        return cudaSuccess;
+    if (algo == ChainAlgo::Replay)
+        k1_chain<true><<<blocks, threads, 0, stream>>>(job);
+    else
+        k1_chain<false><<<blocks, threads, 0, stream>>>(job);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------
+// K2 tuned
+// ------------------------------------------------------------------------------------
+constexpr int kK2Threads = 512;
+
+int synth_threads() { return kK2Threads; }
+
+// shared memory: [lut 512*32 i32][negw 33*33 u32, padded][x f64 [C][T]][phs u32 [C][T]][meta u32 [C][T]]
+constexpr size_t kSmemLut = (size_t)kLutEntries * kLutReplicas * sizeof(int32_t);
+constexpr size_t kSmemNegw = ((size_t)kCaPrns * kCaWords * sizeof(uint32_t) + 15) & ~(size_t)15;
+
+size_t synth_smem_bytes(int max_active, int threads)
+{
+    if (max_active < 1)
+        max_active = 1;
+    return kSmemLut + kSmemNegw + (size_t)max_active * threads * 16;
+}
+
+template <int FMT, int S>
+__global__ void __launch_bounds__(kK2Threads, 1) k2_synth(DeviceJob job)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    int32_t *lut = reinterpret_cast<int32_t *>(smem);
+    uint32_t *negw = reinterpret_cast<uint32_t *>(smem + kSmemLut);
+    double *st_x = reinterpret_cast<double *>(smem + kSmemLut + kSmemNegw);
+    uint32_t *st_phs = reinterpret_cast<uint32_t *>(st_x + (size_t)job.max_active * kK2Threads);
+    uint32_t *st_meta = st_phs + (size_t)job.max_active * kK2Threads;
+
+    const int tid = threadIdx.x;
+    // one replica of the packed carrier table per lane: entry i of lane l at word i*32+l,
+    // so lane l only ever touches bank l
+    for (int i = tid; i < kLutEntries * kLutReplicas; i += kK2Threads)
+        lut[i] = job.lut[i >> 5];
+    for (int i = tid; i < kCaPrns * kCaWords; i += kK2Threads)
+        negw[i] = job.negw[i];
+    __syncthreads();
+
+    const int lane = tid & 31;
+    const int32_t *mylut = lut + lane;
+
+    const long long total = (long long)job.n_epochs * job.kc;
+    const long long gid = (long long)blockIdx.x * kK2Threads + tid;
+    const bool valid = gid < total;
+    const unsigned mask = __ballot_sync(0xffffffffu, valid);
+    if (!valid)
+        return;
+
+    const int e = (int)(gid / job.kc);
+    const int jc = (int)(gid - (long long)e * job.kc);
+    const int n0 = jc * job.chunk;
+    const int nrun = min(job.chunk, job.n_samples - n0);
+    const DevRow *rows = job.rows + (size_t)e * kMaxChan;
+    const int nc = job.nch[e];
+
+    // chunk-start state of every channel
+    for (int k = 0; k < nc; k++) {
+        const size_t ck = ((size_t)e * kMaxChan + k) * job.kc + jc;
+        const DevRow r = rows[k];
+        const int ic = (int)r.icode0 + (int)job.ck_w[ck];
+        st_x[k * kK2Threads + tid] = job.ck_x[ck];
+        st_phs[k * kK2Threads + tid] = (r.ph0 + (uint32_t)n0 * (uint32_t)r.step) << 7;
+        st_meta[k * kK2Threads + tid] = (uint32_t)(ic % 20) | ((uint32_t)(ic / 20) << 8);
+    }
+
+    // warp-wide channel count so that every lane takes part in every vote
+    const int ncw = (int)__reduce_max_sync(mask, (unsigned)nc);
+
+    const int bytes_per_16 = (FMT == 16) ? 64 : (FMT == 8) ? 32 : 4;
+    uint8_t *outp = job.out + (size_t)e * job.epoch_bytes + (size_t)(n0 / 16) * bytes_per_16;
+
+    for (int s0 = 0; s0 < nrun; s0 += S) {
+        int64_t acc[S];
+#pragma unroll
+        for (int j = 0; j < S; j++)
+            acc[j] = kAccBias;
+
+        for (int k = 0; k < ncw; k++) {
+            const bool act = k < nc;
+            ChanState st;
+            DevRow r;
+            bool wrap = false;
+            if (act) {
+                r = rows[k];
+                st.x = st_x[k * kK2Threads + tid];
+                st.phs = st_phs[k * kK2Threads + tid];
+                const uint32_t meta = st_meta[k * kK2Threads + tid];
+                st.icode = (int)(meta & 0xffu);
+                st.bitk = (int)(meta >> 8);
+                // conservative: a whole extra step of margin over the S rounded adds
+                wrap = !(st.x + (double)(S + 1) * r.d < (double)kCaLen) || job.force_wrap_path;
+            }
+            const bool any_wrap = __any_sync(mask, wrap);
+            if (act) {
+                const uint32_t *nw = negw + (size_t)r.prn * kCaWords;
+                const uint32_t steps = (uint32_t)r.step << 7;
+                if (!any_wrap) {
+                    const int32_t g = data_sign(r.nav_bits, st.bitk) * r.gain * (1 << kAccShiftQ);
+                    synth_fast<S>(acc, st, r.d, steps, g, nw, mylut);
+                } else {
+                    synth_wrap<S>(acc, st, r.d, steps, r.gain, r.nav_bits, nw, mylut);
+                    st_meta[k * kK2Threads + tid] = (uint32_t)st.icode | ((uint32_t)st.bitk << 8);
+                }
+                st_x[k * kK2Threads + tid] = st.x;
+                st_phs[k * kK2Threads + tid] = st.phs;
+            }
+        }
+        store_run<FMT, S>(outp + (size_t)(s0 / 16) * bytes_per_16, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K2 generic
+// ------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void __launch_bounds__(128) k2_generic(DeviceJob job)
+{
+    const long long total = (long long)job.n_epochs * job.kc;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total)
+        return;
+    const int e = (int)(gid / job.kc);
+    const int jc = (int)(gid - (long long)e * job.kc);
+    const int n0 = jc * job.chunk;
+    const int nrun = min(job.chunk, job.n_samples - n0);
+    const DevRow *rows = job.rows + (size_t)e * kMaxChan;
+    const int nc = job.nch[e];
+
+    GenericChan ch[kMaxChan];
+    for (int k = 0; k < nc; k++) {
+        const size_t ck = ((size_t)e * kMaxChan + k) * job.kc + jc;
+        const DevRow r = rows[k];
+        const int ic = (int)r.icode0 + (int)job.ck_w[ck];
+        ch[k].x = job.ck_x[ck];
+        ch[k].d = r.d;
+        ch[k].ph = r.ph0 + (uint32_t)n0 * (uint32_t)r.step;
+        ch[k].step = r.step;
+        ch[k].gain = r.gain;
+        ch[k].icode = ic % 20;
+        ch[k].bitk = ic / 20;
+        ch[k].nav_bits = r.nav_bits;
+        ch[k].negw = job.negw + (size_t)r.prn * kCaWords;
+    }
+
+    uint8_t *base = job.out + (size_t)e * job.epoch_bytes;
+    uint32_t byte = 0;
+    for (int n = 0; n < nrun; n++) {
+        int i16, q16;
+        generic_sample(ch, nc, job.sin16, job.cos16, i16, q16);
+        const int s = n0 + n;
+        if (FMT == 16) {
+            reinterpret_cast<uint32_t *>(base)[s] = ((uint32_t)i16 & 0xffffu) | ((uint32_t)q16 << 16);
+        } else if (FMT == 8) {
+            reinterpret_cast<uint16_t *>(base)[s] =
+                (uint16_t)(((uint32_t)(i16 >> 4) & 0xffu) | (((uint32_t)(q16 >> 4) & 0xffu) << 8));
+        } else {
+            byte = (byte << 2) | (i16 > 0 ? 2u : 0u) | (q16 > 0 ? 1u : 0u);
+            if ((s & 3) == 3) {
+                if ((s >> 2) < job.n_samples / 4) // the reference writes floor(N/4) bytes (gpssim.c:2276)
+                    base[s >> 2] = (uint8_t)byte;
+                byte = 0;
+            }
+        }
+    }
+}
+
+template <int FMT, int S>
+static cudaError_t launch_tuned(const DeviceJob &job, cudaStream_t stream)
+{
+    const size_t smem = synth_smem_bytes(job.max_active, kK2Threads);
+    cudaError_t err = cudaFuncSetAttribute(k2_synth<FMT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess)
+        return err;
+    const long long total = (long long)job.n_epochs * job.kc;
+    const int blocks = (int)((total + kK2Threads - 1) / kK2Threads);
+    k2_synth<FMT, S><<<blocks, kK2Threads, smem, stream>>>(job);
+    return cudaGetLastError();
+}
+
+template <int FMT>
+static cudaError_t launch_generic(const DeviceJob &job, cudaStream_t stream)
+{
+    const long long total = (long long)job.n_epochs * job.kc;
+    const int threads = 128;
+    const int blocks = (int)((total + threads - 1) / threads);
+    k2_generic<FMT><<<blocks, threads, 0, stream>>>(job);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_synth(const DeviceJob &job, SynthKernel which, cudaStream_t stream)
+{
+    if (job.n_epochs == 0)
+        return cudaSuccess;
+#define GS_DISPATCH(FMTV)                                                        \
+    if (which == SynthKernel::Tuned32) return launch_tuned<FMTV, 32>(job, stream); \
+    if (which == SynthKernel::Tuned16) return launch_tuned<FMTV, 16>(job, stream); \
+    return launch_generic<FMTV>(job, stream);
+    if (job.fmt == 16) { GS_DISPATCH(16) }
+    if (job.fmt == 8) { GS_DISPATCH(8) }
+    GS_DISPATCH(1)
+#undef GS_DISPATCH
+}
+
+} // namespace gpusim

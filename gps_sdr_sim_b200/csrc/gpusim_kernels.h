@@ -1,0 +1,47 @@
+// gpusim_kernels.h - launch interface between the C ABI (gpusim_api.cu) and the kernels.
+#ifndef GPUSIM_KERNELS_H
+#define GPUSIM_KERNELS_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gpusim_core.h"
+
+namespace gpusim {
+
+// Everything the kernels read for one generate call.  All pointers are device memory.
+// "rel" epochs: rows/nch/x0/out are already offset to the first epoch of the range.
+struct DeviceJob {
+    const DevRow *rows;      // [n_epochs][16], active channels compacted to the front
+    const uint8_t *nch;      // [n_epochs] active channel count
+    const double *x0;        // [n_epochs][16] code_phase at epoch start
+    double *ck_x;            // [n_epochs][16][kc] code phase at sample j*chunk
+    uint16_t *ck_w;          // [n_epochs][16][kc] 1023-chip wraps before sample j*chunk
+    const int32_t *lut;      // [512] packed carrier table words (lut_word)
+    const int16_t *sin16;    // [512] plain tables for the generic kernel
+    const int16_t *cos16;    // [512]
+    const uint32_t *negw;    // [33][33] inverted C/A chips per PRN
+    uint8_t *out;            // n_epochs * epoch_bytes
+    int32_t n_epochs;
+    int32_t n_samples;       // samples per epoch
+    int32_t chunk;           // samples per thread chunk (multiple of 32)
+    int32_t kc;              // chunks per epoch = ceil(n_samples/chunk)
+    int32_t fmt;             // 1 / 8 / 16
+    int32_t epoch_bytes;
+    int32_t max_active;      // max nch over the range (sizes the per-thread state)
+    int32_t force_wrap_path; // test hook: always run the wrap-checking loop
+};
+
+enum class ChainAlgo { Jump = 0, Replay = 1 };
+enum class SynthKernel { Tuned32 = 0, Tuned16 = 1, Generic = 2 };
+
+// K1: exact code-phase checkpoints for every (epoch, active channel, chunk)
+cudaError_t launch_chain(const DeviceJob &job, ChainAlgo algo, cudaStream_t stream);
+// K2: samples -> bytes
+cudaError_t launch_synth(const DeviceJob &job, SynthKernel which, cudaStream_t stream);
+// dynamic shared memory the tuned kernel needs for a given max_active (0 if it cannot run)
+size_t synth_smem_bytes(int max_active, int threads);
+int synth_threads();
+
+} // namespace gpusim
+#endif

@@ -1,0 +1,200 @@
+// emu.cpp - runs the device algorithms of gps_sdr_sim_b200/csrc/gpusim_core.h thread by
+// thread on the CPU.  TEST INFRASTRUCTURE ONLY: it lets the CPU test-suite compare the
+// exact code the kernels execute (chain walk, packed accumulator, wrap handling, packing)
+// with the oracle before any GPU time is spent.  The product never loads this.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "gpusim.h"
+#include "gpusim_core.h"
+#include "gpusim_tables.h"
+
+using namespace gpusim;
+
+namespace {
+
+struct Tables {
+    std::vector<int32_t> lut;   // [512][32] replicated like the kernel's shared memory
+    std::vector<int16_t> s16, c16;
+    std::vector<uint32_t> negw; // [33][33]
+    Tables() : lut(512 * 32), s16(512), c16(512), negw(kCaPrns * kCaWords, 0xffffffffu)
+    {
+        int32_t s[512], c[512];
+        carrier_lut(s, c);
+        for (int i = 0; i < 512; i++) {
+            for (int l = 0; l < 32; l++)
+                lut[i * 32 + l] = lut_word(c[i], s[i]);
+            s16[i] = (int16_t)s[i];
+            c16[i] = (int16_t)c[i];
+        }
+        for (int prn = 1; prn <= 32; prn++) {
+            uint32_t w[kCaWords];
+            ca_words(prn, w);
+            for (int i = 0; i < kCaWords; i++)
+                negw[prn * kCaWords + i] = ~w[i];
+        }
+    }
+};
+
+template <int FMT, int S>
+void tuned_chunk(const Tables &T, const DevRow *rows, int nc, const double *ckx, const uint16_t *ckw, int kc,
+                 int jc, int chunk, int N, int force_wrap, int lane, uint8_t *epoch_out)
+{
+    const int n0 = jc * chunk;
+    const int nrun = std::min(chunk, N - n0);
+    ChanState st[kMaxChan];
+    for (int k = 0; k < nc; k++) {
+        const int ic = rows[k].icode0 + ckw[k * kc + jc];
+        st[k].x = ckx[k * kc + jc];
+        st[k].phs = (rows[k].ph0 + (uint32_t)n0 * (uint32_t)rows[k].step) << 7;
+        st[k].icode = ic % 20;
+        st[k].bitk = ic / 20;
+    }
+    const int bytes_per_16 = (FMT == 16) ? 64 : (FMT == 8) ? 32 : 4;
+    uint8_t *outp = epoch_out + (size_t)(n0 / 16) * bytes_per_16;
+    const int32_t *mylut = T.lut.data() + lane;
+    for (int s0 = 0; s0 < nrun; s0 += S) {
+        int64_t acc[S];
+        for (int j = 0; j < S; j++)
+            acc[j] = kAccBias;
+        for (int k = 0; k < nc; k++) {
+            const DevRow &r = rows[k];
+            const bool wrap = !(st[k].x + (double)(S + 1) * r.d < (double)kCaLen) || force_wrap;
+            const uint32_t *nw = T.negw.data() + (size_t)r.prn * kCaWords;
+            const uint32_t steps = (uint32_t)r.step << 7;
+            if (!wrap) {
+                const int32_t g = data_sign(r.nav_bits, st[k].bitk) * r.gain * (1 << kAccShiftQ);
+                synth_fast<S>(acc, st[k], r.d, steps, g, nw, mylut);
+            } else {
+                synth_wrap<S>(acc, st[k], r.d, steps, r.gain, r.nav_bits, nw, mylut);
+            }
+        }
+        store_run<FMT, S>(outp + (size_t)(s0 / 16) * bytes_per_16, acc);
+    }
+}
+
+template <int FMT>
+void generic_chunk(const Tables &T, const DevRow *rows, int nc, const double *ckx, const uint16_t *ckw, int kc,
+                   int jc, int chunk, int N, uint8_t *base)
+{
+    const int n0 = jc * chunk;
+    const int nrun = std::min(chunk, N - n0);
+    GenericChan ch[kMaxChan];
+    for (int k = 0; k < nc; k++) {
+        const DevRow &r = rows[k];
+        const int ic = r.icode0 + ckw[k * kc + jc];
+        ch[k].x = ckx[k * kc + jc];
+        ch[k].d = r.d;
+        ch[k].ph = r.ph0 + (uint32_t)n0 * (uint32_t)r.step;
+        ch[k].step = r.step;
+        ch[k].gain = r.gain;
+        ch[k].icode = ic % 20;
+        ch[k].bitk = ic / 20;
+        ch[k].nav_bits = r.nav_bits;
+        ch[k].negw = T.negw.data() + (size_t)r.prn * kCaWords;
+    }
+    uint32_t byte = 0;
+    for (int n = 0; n < nrun; n++) {
+        int i16, q16;
+        generic_sample(ch, nc, T.s16.data(), T.c16.data(), i16, q16);
+        const int s = n0 + n;
+        if (FMT == 16) {
+            const uint32_t w = ((uint32_t)i16 & 0xffffu) | ((uint32_t)q16 << 16);
+            memcpy(base + 4 * (size_t)s, &w, 4);
+        } else if (FMT == 8) {
+            const uint16_t w = (uint16_t)(((uint32_t)(i16 >> 4) & 0xffu) | (((uint32_t)(q16 >> 4) & 0xffu) << 8));
+            memcpy(base + 2 * (size_t)s, &w, 2);
+        } else {
+            byte = (byte << 2) | (i16 > 0 ? 2u : 0u) | (q16 > 0 ? 1u : 0u);
+            if ((s & 3) == 3) {
+                if ((s >> 2) < N / 4)
+                    base[s >> 2] = (uint8_t)byte;
+                byte = 0;
+            }
+        }
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+// kernel: 0 = tuned S=32, 1 = tuned S=16, 2 = generic.  Returns 0, or -1 if the table is outside
+// the selected kernel's documented ranges.
+int emu_generate(const gpusim_epoch_table *t, int N, double delt, int fmt, int chunk, int kernel,
+                 int force_wrap, int chain_replay, uint8_t *out)
+{
+    static const Tables T;
+    const size_t eb = fmt == 1 ? (size_t)(N / 4) : fmt == 8 ? (size_t)2 * N : (size_t)4 * N;
+    const int kc = (N + chunk - 1) / chunk;
+    if (chunk % 32 != 0 || (kernel != 2 && N % 32 != 0))
+        return -1;
+    std::vector<double> ckx((size_t)kMaxChan * kc);
+    std::vector<uint16_t> ckw((size_t)kMaxChan * kc);
+    for (int e = 0; e < t->n_epochs; e++) {
+        DevRow rows[kMaxChan];
+        double x0[kMaxChan];
+        int nc = 0;
+        for (int i = 0; i < kMaxChan; i++) {
+            const size_t r = (size_t)e * kMaxChan + i;
+            if (t->prn[r] <= 0)
+                continue;
+            DevRow &o = rows[nc];
+            o.d = dmul(t->f_code[r], delt);
+            o.ph0 = t->carr_phase[r];
+            o.step = t->carr_phasestep[r];
+            o.gain = t->gain[r];
+            o.nav_bits = t->nav_bits[r];
+            o.prn = (uint16_t)t->prn[r];
+            o.icode0 = (uint16_t)t->icode[r];
+            o.flags = 0;
+            if (kernel != 2 && (o.gain < 0 || o.gain > kTunedMaxGain || o.d > (kernel == 0 ? 0.9999 : 2.0)))
+                return -1;
+            x0[nc++] = t->code_phase[r];
+        }
+        for (int k = 0; k < nc; k++) {
+            double *cx = ckx.data() + (size_t)k * kc;
+            uint16_t *cw = ckw.data() + (size_t)k * kc;
+            auto emit = [&](int j, double x, int wraps) {
+                cx[j] = x;
+                cw[j] = (uint16_t)wraps;
+            };
+            if (chain_replay)
+                code_chain_replay(x0[k], rows[k].d, N, chunk, emit);
+            else
+                code_chain(x0[k], rows[k].d, N, chunk, emit);
+        }
+        uint8_t *eo = out + (size_t)e * eb;
+        for (int jc = 0; jc < kc; jc++) {
+            const int lane = jc & 31;
+#define EMU_TUNED(F, S) tuned_chunk<F, S>(T, rows, nc, ckx.data(), ckw.data(), kc, jc, chunk, N, force_wrap, lane, eo)
+            if (kernel == 0) {
+                if (fmt == 16) EMU_TUNED(16, 32); else if (fmt == 8) EMU_TUNED(8, 32); else EMU_TUNED(1, 32);
+            } else if (kernel == 1) {
+                if (fmt == 16) EMU_TUNED(16, 16); else if (fmt == 8) EMU_TUNED(8, 16); else EMU_TUNED(1, 16);
+            } else {
+                if (fmt == 16) generic_chunk<16>(T, rows, nc, ckx.data(), ckw.data(), kc, jc, chunk, N, eo);
+                else if (fmt == 8) generic_chunk<8>(T, rows, nc, ckx.data(), ckw.data(), kc, jc, chunk, N, eo);
+                else generic_chunk<1>(T, rows, nc, ckx.data(), ckw.data(), kc, jc, chunk, N, eo);
+            }
+#undef EMU_TUNED
+        }
+    }
+    return 0;
+}
+
+// the chain walk alone: checkpoints every `every` samples
+void emu_code_chain(double x0, double d, int n_total, int every, int replay, double *x_out, int *w_out)
+{
+    auto emit = [&](int j, double x, int wraps) {
+        x_out[j] = x;
+        w_out[j] = wraps;
+    };
+    if (replay)
+        code_chain_replay(x0, d, n_total, every, emit);
+    else
+        code_chain(x0, d, n_total, every, emit);
+}
+
+} // extern "C"

@@ -1,0 +1,59 @@
+"""ctypes access to tests/emu/libgpusim_emu.so: the device algorithms run on the CPU.
+TEST INFRASTRUCTURE ONLY."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+CSRC = os.path.join(ROOT, "gps_sdr_sim_b200", "csrc")
+_lib = None
+
+TUNED32, TUNED16, GENERIC = 0, 1, 2
+
+
+def build() -> str:
+    so = os.path.join(EMU_DIR, "libgpusim_emu.so")
+    deps = [os.path.join(EMU_DIR, "emu.cpp"), os.path.join(CSRC, "gpusim_core.h"),
+            os.path.join(CSRC, "gpusim_tables.cpp"), os.path.join(CSRC, "gpusim_tables.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall",
+                        "-Wno-unknown-pragmas", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+                        deps[0], deps[2], "-o", so], check=True, capture_output=True)
+    return so
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.emu_generate.restype = ctypes.c_int
+        _lib.emu_generate.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        _lib.emu_code_chain.restype = None
+        _lib.emu_code_chain.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_void_p, ctypes.c_void_p]
+    return _lib
+
+
+def generate(table, chunk: int = 512, kernel: int = TUNED32, force_wrap: bool = False,
+             chain_replay: bool = False) -> np.ndarray:
+    out = np.zeros(table.n_epochs * table.epoch_bytes, dtype=np.uint8)
+    c = table.as_c()
+    rc = lib().emu_generate(ctypes.addressof(c), table.samples_per_epoch, table.delt, table.data_format, chunk,
+                            kernel, int(force_wrap), int(chain_replay), out.ctypes.data)
+    if rc != 0:
+        raise ValueError("table outside the selected kernel's ranges")
+    return out
+
+
+def code_chain(x0: float, d: float, n: int, every: int, replay: bool = False):
+    k = (n + every - 1) // every
+    x = np.empty(k, dtype=np.float64)
+    w = np.empty(k, dtype=np.int32)
+    lib().emu_code_chain(x0, d, n, every, int(replay), x.ctypes.data, w.ctypes.data)
+    return x, w

@@ -1,0 +1,55 @@
+"""K1: the binade-jump walk of the code-phase chain equals the reference's N sequential adds."""
+import numpy as np
+import pytest
+
+import emu_lib
+import oracle_lib
+
+
+def _cases():
+    rng = np.random.default_rng(20141220)
+    cases = []
+    for fs, n in ((1.0e6, 100000), (2.6e6, 260000), (4.0e6, 400000), (20.0e6, 2000000)):
+        delt = 1.0 / fs
+        for _ in range(6 if n < 1000000 else 2):
+            f_code = 1.023e6 + rng.uniform(-30.0, 30.0)
+            x0 = rng.uniform(0.0, 1023.0)
+            cases.append((x0, f_code, delt, n))
+        # start right below the wrap, at zero, and in the tiny binades just above zero
+        cases.append((np.nextafter(1023.0, 0.0), 1.023e6 + 3.0, delt, n))
+        cases.append((0.0, 1.023e6 - 28.5, delt, n))
+        cases.append((2.0 ** -30, 1.023e6 + 28.5, delt, n))
+    return cases
+
+
+@pytest.mark.parametrize("x0,f_code,delt,n", _cases())
+def test_jump_chain_equals_sequential_replay(x0, f_code, delt, n):
+    d = float(np.float64(f_code) * np.float64(delt))       # the reference's rounded product
+    for every in (128, 512, 4096):
+        xo, wo = oracle_lib.code_phase_checkpoints(x0, f_code, delt, n, every)
+        xj, wj = emu_lib.code_chain(x0, d, n, every, replay=False)
+        assert np.array_equal(xo.view(np.uint64), xj.view(np.uint64)), every   # bit-exact doubles
+        assert np.array_equal(wo, wj)
+
+
+def test_tie_increments_are_handled():
+    # d with a significand that is an exact half-ulp tie in the binades above it
+    rng = np.random.default_rng(3)
+    for shift in range(1, 12):
+        mant = (int(rng.integers(1 << 51, 1 << 52)) >> shift << shift) | (1 << (shift - 1)) | (1 << 52)
+        d = float(np.ldexp(np.float64(mant), -54))          # in [0.25, 0.5)
+        for x0 in (0.3, 1.5, 700.0):
+            n = 20000
+            # oracle takes f_code and delt; use delt = 1 so f_code*delt == d exactly
+            xo, wo = oracle_lib.code_phase_checkpoints(x0, d, 1.0, n, 256)
+            xj, wj = emu_lib.code_chain(x0, d, n, 256)
+            assert np.array_equal(xo.view(np.uint64), xj.view(np.uint64)), (shift, x0)
+            assert np.array_equal(wo, wj)
+
+
+def test_replay_variant_matches_too():
+    x0, f_code, delt, n = 511.25, 1.023e6 + 1.5, 1 / 2.6e6, 260000
+    d = float(np.float64(f_code) * np.float64(delt))
+    xo, wo = oracle_lib.code_phase_checkpoints(x0, f_code, delt, n, 512)
+    xr, wr = emu_lib.code_chain(x0, d, n, 512, replay=True)
+    assert np.array_equal(xo.view(np.uint64), xr.view(np.uint64)) and np.array_equal(wo, wr)

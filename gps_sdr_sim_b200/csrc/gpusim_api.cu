@@ -38,6 +38,7 @@ struct gpusim_ctx {
 
     // constant tables
     int32_t *d_lut = nullptr;
+    uint64_t *d_lut_f32 = nullptr;
     int16_t *d_sin16 = nullptr, *d_cos16 = nullptr;
     uint32_t *d_negw = nullptr;
 
@@ -59,7 +60,7 @@ struct gpusim_ctx {
     uint8_t *h_stage[2] = {nullptr, nullptr};
 
     // options
-    int opt_chunk = 0, opt_force_generic = 0, opt_force_slow = 0, opt_chain_replay = 0;
+    int opt_chunk = 0, opt_force_generic = 0, opt_force_slow = 0, opt_chain_replay = 0, opt_accum = 0;
 
     gpusim_timing timing{};
 };
@@ -127,7 +128,9 @@ int launch_range(gpusim_ctx *ctx, int first, int n, uint8_t *out_dev, cudaStream
     job.x0 = ctx->d_x0 + (size_t)first * kMaxChan;
     job.ck_x = ctx->d_ck_x;
     job.ck_w = ctx->d_ck_w;
-    job.lut = ctx->d_lut;
+    job.lut_wide = ctx->d_lut;
+    job.lut_f32 = ctx->d_lut_f32;
+    job.accum = ctx->opt_accum;
     job.sin16 = ctx->d_sin16;
     job.cos16 = ctx->d_cos16;
     job.negw = ctx->d_negw;
@@ -204,7 +207,7 @@ void gpusim_destroy(gpusim_ctx *ctx)
     cudaSetDevice(ctx->cfg.device);
     if (ctx->s_compute) cudaStreamSynchronize(ctx->s_compute);
     if (ctx->s_copy) cudaStreamSynchronize(ctx->s_copy);
-    cudaFree(ctx->d_lut); cudaFree(ctx->d_sin16); cudaFree(ctx->d_cos16); cudaFree(ctx->d_negw);
+    cudaFree(ctx->d_lut); cudaFree(ctx->d_lut_f32); cudaFree(ctx->d_sin16); cudaFree(ctx->d_cos16); cudaFree(ctx->d_negw);
     cudaFree(ctx->d_rows); cudaFree(ctx->d_nch); cudaFree(ctx->d_x0);
     cudaFree(ctx->d_ck_x); cudaFree(ctx->d_ck_w); cudaFree(ctx->d_out);
     cudaFreeHost(ctx->h_rows); cudaFreeHost(ctx->h_nch); cudaFreeHost(ctx->h_x0);
@@ -271,10 +274,12 @@ int gpusim_create(const gpusim_config *cfg, gpusim_ctx **out_ctx)
     // constant tables
     {
         int32_t s[512], c[512], lut[512];
+        uint64_t lut2[512];
         int16_t s16[512], c16[512];
         carrier_lut(s, c);
         for (int i = 0; i < 512; i++) {
-            lut[i] = lut_word(c[i], s[i]);
+            lut[i] = AccWide::table_entry(c[i], s[i]);
+            lut2[i] = AccF32x2::table_entry(c[i], s[i]);
             s16[i] = (int16_t)s[i];
             c16[i] = (int16_t)c[i];
         }
@@ -286,6 +291,8 @@ int gpusim_create(const gpusim_config *cfg, gpusim_ctx **out_ctx)
                 negw[(size_t)prn * kCaWords + i] = ~w[i]; // bit set = chip 0 = codeCA -1 (gpssim.c:2241)
         }
         GS_CREATE(cudaMalloc(&ctx->d_lut, sizeof(lut)));
+        GS_CREATE(cudaMalloc(&ctx->d_lut_f32, sizeof(lut2)));
+        GS_CREATE(cudaMemcpy(ctx->d_lut_f32, lut2, sizeof(lut2), cudaMemcpyHostToDevice));
         GS_CREATE(cudaMalloc(&ctx->d_sin16, sizeof(s16)));
         GS_CREATE(cudaMalloc(&ctx->d_cos16, sizeof(c16)));
         GS_CREATE(cudaMalloc(&ctx->d_negw, negw.size() * sizeof(uint32_t)));
@@ -324,6 +331,7 @@ int gpusim_set_option(gpusim_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "force_generic")) ctx->opt_force_generic = (int)value;
     else if (!strcmp(key, "force_slow")) ctx->opt_force_slow = (int)value;
     else if (!strcmp(key, "chain_replay")) ctx->opt_chain_replay = (int)value;
+    else if (!strcmp(key, "accum")) ctx->opt_accum = (int)value;
     else return fail(ctx, GPUSIM_ERR_ARG, "unknown option '%s'", key);
     return GPUSIM_OK;
 }

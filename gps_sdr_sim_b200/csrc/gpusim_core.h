@@ -31,7 +31,7 @@ namespace gpusim {
 constexpr int kMaxChan = 16;
 constexpr int kCaLen = 1023;
 constexpr int kLutEntries = 512;
-constexpr int kLutReplicas = 32;     // one copy per lane: every LDS is conflict free
+constexpr int kLutBytes = 512 * 128;  // replicated carrier table: 512 entries, 128 bytes apart
 constexpr int kCaWords = 33;         // per PRN, see gpusim_tables.h
 constexpr int kCaPrns = 33;          // index by prn 0..32 (0 unused)
 
@@ -118,21 +118,84 @@ struct alignas(16) DevRow {
 static_assert(sizeof(DevRow) == 32, "DevRow layout");
 
 constexpr uint32_t kRowNeedsGeneric = 1u;
-constexpr int kTunedMaxGain = 255; // 16 ch * 250 * 255 + 64 < 2^20, see kAccBias
+constexpr int kTunedMaxGain = 255; // 16 ch * 250 * 255 + 64 < 2^20: the accumulator fields below hold it
 
-// ---- packed accumulator of the tuned kernel -----------------------------------------
-// One 32-bit table word T = cos*2^21 + sin; multiplier g = dataBit*gain*2^4.
-// T*g = (cos*dataBit*gain)<<25 + (sin*dataBit*gain)<<4 accumulates I and Q in ONE
-// 64-bit multiply-add.  Both fields carry a bias of 2^20+64 so they never go negative
-// (no borrow between fields) and the +64 of "(acc+64)>>7" is already inside:
-//   bits 32..45 of acc = ((i_acc+64)>>7) + 8192,  bits 11..24 = ((q_acc+64)>>7) + 8192.
-constexpr int kAccShiftQ = 4;
-constexpr int kAccShiftI = 25;
-constexpr int64_t kFieldBias = (1 << 20) + 64;
-constexpr int64_t kAccBias = (kFieldBias << kAccShiftI) + (kFieldBias << kAccShiftQ);
-GS_HD int32_t lut_word(int cosv, int sinv) { return cosv * (1 << 21) + sinv; }
-GS_HD int32_t acc_i_biased(int64_t acc) { return (int32_t)(acc >> 32); }                   // I16 + 8192
-GS_HD int32_t acc_q_biased(int64_t acc) { return (int32_t)(((uint32_t)acc >> 11) & 0x3fffu); } // Q16 + 8192
+// ---- accumulator policies of the tuned kernel -----------------------------------------
+// Both keep the I and the Q sum of one sample in ONE 64-bit register pair and add a
+// channel with ONE instruction; both expose the sums as "biased" integers
+//     i_biased = ((i_acc + 64) >> 7) + 8192,   q_biased likewise   (gpssim.c:2258-2259)
+// which the packers below turn into SC16 / SC08 / SC01 bytes.  The carrier table is
+// replicated in shared memory so that a lookup never has a bank conflict: entries are
+// 128 bytes apart and the replica is chosen by the lane, byte offset
+//     ((e >> 16) & 0xff80) | lane_off            e = phase with the chip sign folded in.
+
+// (1) 64-bit integer multiply-add on a packed 32-bit table word.
+//     T = cos*2^21 + sin, g = dataBit*gain*2^4:  T*g = (cos*dataBit*gain)<<25 + (sin*dataBit*gain)<<4.
+//     Both fields carry a bias of 2^20+64: never negative (no borrow between fields), and the
+//     +64 of the rounding is already inside.  32 replicas x 4 bytes.
+struct AccWide {
+    typedef int64_t acc_t;
+    typedef int32_t tab_t;
+    typedef int32_t gain_t;
+    static constexpr int kLaneMask = 31, kLaneShift = 2;
+    static constexpr int kShiftQ = 4, kShiftI = 25;
+    static constexpr int64_t kFieldBias = (1 << 20) + 64;
+    static GS_HD acc_t init() { return (kFieldBias << kShiftI) + (kFieldBias << kShiftQ); }
+    static GS_HD tab_t table_entry(int cosv, int sinv) { return cosv * (1 << 21) + sinv; }
+    static GS_HD gain_t make_gain(int signed_gain) { return signed_gain * (1 << kShiftQ); }
+    static GS_HD void mad(acc_t &acc, tab_t t, gain_t g) { acc = mad_wide(t, g, acc); }
+    static GS_HD int32_t i_biased(acc_t acc) { return (int32_t)(acc >> 32); }
+    static GS_HD int32_t q_biased(acc_t acc) { return (int32_t)(((uint32_t)acc >> 11) & 0x3fffu); }
+};
+
+// (2) packed fp32x2 FMA (Blackwell FFMA2) on a float2 table entry (cos, sin).  All values are
+//     integers below 2^24, so fp32 arithmetic is exact.  The accumulator starts at
+//     1.5*2^23 + 64: its mantissa bits then hold (sum + 64) in two's complement, no conversion
+//     instruction needed.  16 replicas x 8 bytes (a 64-bit LDS is served per half warp).
+struct AccF32x2 {
+    typedef uint64_t acc_t;
+    typedef uint64_t tab_t;
+    typedef uint64_t gain_t;
+    static constexpr int kLaneMask = 15, kLaneShift = 3;
+    static constexpr uint32_t kMagicBits = 0x4b400000u; // 12582912.0f
+    static GS_HD uint32_t fbits(float f)
+    {
+#ifdef __CUDA_ARCH__
+        return __float_as_uint(f);
+#else
+        uint32_t u;
+        memcpy(&u, &f, 4);
+        return u;
+#endif
+    }
+    static GS_HD float ffrom(uint32_t u)
+    {
+#ifdef __CUDA_ARCH__
+        return __uint_as_float(u);
+#else
+        float f;
+        memcpy(&f, &u, 4);
+        return f;
+#endif
+    }
+    static GS_HD uint64_t pack(float lo, float hi) { return (uint64_t)fbits(lo) | ((uint64_t)fbits(hi) << 32); }
+    static GS_HD acc_t init() { return pack(12582976.0f, 12582976.0f); }
+    static GS_HD tab_t table_entry(int cosv, int sinv) { return pack((float)cosv, (float)sinv); }
+    static GS_HD gain_t make_gain(int signed_gain) { return pack((float)signed_gain, (float)signed_gain); }
+    static GS_HD void mad(acc_t &acc, tab_t t, gain_t g)
+    {
+#ifdef __CUDA_ARCH__
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(t), "l"(g));
+#else
+        const float lo = ffrom((uint32_t)t) * ffrom((uint32_t)g) + ffrom((uint32_t)acc);
+        const float hi = ffrom((uint32_t)(t >> 32)) * ffrom((uint32_t)(g >> 32)) + ffrom((uint32_t)(acc >> 32));
+        acc = pack(lo, hi);
+#endif
+    }
+    // mantissa bits = sum + 64 (two's complement around the magic); +2^20 keeps the shift unsigned
+    static GS_HD int32_t i_biased(acc_t acc) { return (int32_t)(((uint32_t)acc - kMagicBits + (1u << 20)) >> 7); }
+    static GS_HD int32_t q_biased(acc_t acc) { return (int32_t)(((uint32_t)(acc >> 32) - kMagicBits + (1u << 20)) >> 7); }
+};
 
 // =====================================================================================
 // K1 - code-phase chain.  The reference advances code_phase by N rounded double adds per
@@ -235,15 +298,22 @@ GS_HD int data_sign(uint32_t nav_bits, int bitk) // +1 / -1, gpssim.c:2236
 //
 //   x      code phase of the first sample (chips)          d      per-sample addend
 //   phs    carr_phase << 7 (table index = phs >> 23)        steps  carr_phasestep << 7
-//   g      dataBit*gain << kAccShiftQ
 //   negw   this PRN's chips, INVERTED (bit set = chip 0 = codeCA -1), 33 words, MSB first
-//   lut    this lane's replica of the packed table: entry i at lut[i*kLutReplicas]
+//   lut    the replicated carrier table in shared memory, lane_off this lane's replica
 //
 // The chip sign is folded into the carrier phase: negating (cos,sin) equals adding half
-// a cycle, i.e. flipping bit 31 of phs (sin[i^256] == -sin[i] for this table), so a
-// sample costs: 2 FP64 adds (advance x; floor(x)-c0 via a round-down magic add), a shift
-// of the chip window, one LOP3, one shift, one conflict-free LDS and one 64-bit IMAD.
+// a cycle, i.e. flipping bit 31 of phs (sin[i^256] == -sin[i] for this table).  A sample
+// of a channel then costs 2 FP64 adds (advance x; floor(x)-c0 through a round-down magic
+// add), a shift of the 32-chip window, one LOP3 (xor), one shift, one LOP3 (mask|lane),
+// one conflict-free LDS, one multiply-add for I and Q together, one add for the carrier.
 // =====================================================================================
+template <class A>
+GS_HD typename A::tab_t lut_at(const typename A::tab_t *lut, uint32_t e, uint32_t lane_off)
+{
+    const uint32_t off = ((e >> 16) & 0xff80u) | lane_off; // (table index << 7) | replica, bytes
+    return *reinterpret_cast<const typename A::tab_t *>(reinterpret_cast<const char *>(lut) + off);
+}
+
 struct ChanState {
     double x;
     uint32_t phs;
@@ -251,20 +321,22 @@ struct ChanState {
     int32_t bitk;  // data bits consumed since the row
 };
 
-template <int S>
-GS_HD void synth_fast(int64_t (&acc)[S], ChanState &st, const double d, const uint32_t steps,
-                      const int32_t g, const uint32_t *negw, const int32_t *lut)
+template <class A, int S>
+GS_HD void synth_fast(typename A::acc_t (&acc)[S], ChanState &st, const double d, const uint32_t steps,
+                      const int signed_gain, const uint32_t *negw, const typename A::tab_t *lut,
+                      const uint32_t lane_off)
 {
     double x = st.x;
     uint32_t phs = st.phs;
     const int c0 = (int)x;
     const uint32_t win = funnel_l(negw[(c0 >> 5) + 1], negw[c0 >> 5], (uint32_t)c0 & 31u);
     const double magic = 4503599627370496.0 - (double)c0;
+    const typename A::gain_t g = A::make_gain(signed_gain);
 #pragma unroll
     for (int j = 0; j < S; j++) {
         const uint32_t adv = chips_since(x, magic);
         const uint32_t e = phs ^ ((win << adv) & 0x80000000u);
-        acc[j] = mad_wide(lut[(e >> 23) * kLutReplicas], g, acc[j]);
+        A::mad(acc[j], lut_at<A>(lut, e, lane_off), g);
         x = dadd(x, d);
         phs += steps;
     }
@@ -274,22 +346,22 @@ GS_HD void synth_fast(int64_t (&acc)[S], ChanState &st, const double d, const ui
 
 // Same samples, but the 1023-chip wrap (and with it the icode / data-bit walk of
 // gpssim.c:2214-2238) may happen inside the run.
-template <int S>
-GS_HD void synth_wrap(int64_t (&acc)[S], ChanState &st, const double d, const uint32_t steps,
+template <class A, int S>
+GS_HD void synth_wrap(typename A::acc_t (&acc)[S], ChanState &st, const double d, const uint32_t steps,
                       const int32_t gain, const uint32_t nav_bits, const uint32_t *negw,
-                      const int32_t *lut)
+                      const typename A::tab_t *lut, const uint32_t lane_off)
 {
     double x = st.x;
     uint32_t phs = st.phs;
     int c0 = (int)x;
     uint32_t win = funnel_l(negw[(c0 >> 5) + 1], negw[c0 >> 5], (uint32_t)c0 & 31u);
     double magic = 4503599627370496.0 - (double)c0;
-    int32_t g = data_sign(nav_bits, st.bitk) * gain * (1 << kAccShiftQ);
+    typename A::gain_t g = A::make_gain(data_sign(nav_bits, st.bitk) * gain);
 #pragma unroll
     for (int j = 0; j < S; j++) {
         const uint32_t adv = chips_since(x, magic);
         const uint32_t e = phs ^ ((win << adv) & 0x80000000u);
-        acc[j] = mad_wide(lut[(e >> 23) * kLutReplicas], g, acc[j]);
+        A::mad(acc[j], lut_at<A>(lut, e, lane_off), g);
         x = dadd(x, d);
         phs += steps;
         if (x >= (double)kCaLen) {
@@ -297,7 +369,7 @@ GS_HD void synth_wrap(int64_t (&acc)[S], ChanState &st, const double d, const ui
             if (++st.icode >= 20) {
                 st.icode = 0;
                 st.bitk++;
-                g = data_sign(nav_bits, st.bitk) * gain * (1 << kAccShiftQ);
+                g = A::make_gain(data_sign(nav_bits, st.bitk) * gain);
             }
             win = negw[0];
             magic = 4503599627370496.0;
@@ -307,22 +379,18 @@ GS_HD void synth_wrap(int64_t (&acc)[S], ChanState &st, const double d, const ui
     st.phs = phs;
 }
 
-// ---- output packing (gpssim.c:2258-2288) from the biased accumulator -----------------
-GS_HD uint32_t pack_sc16(int64_t acc) // little-endian short I, short Q
+// ---- output packing (gpssim.c:2258-2288) from the biased sums -------------------------
+GS_HD uint32_t pack_sc16(int32_t ib, int32_t qb) // little-endian short I, short Q
 {
-    const uint32_t i16 = (uint32_t)(acc_i_biased(acc) - 8192) & 0xffffu;
-    const uint32_t q16 = (uint32_t)(acc_q_biased(acc) - 8192) & 0xffffu;
-    return i16 | (q16 << 16);
+    return ((uint32_t)(ib - 8192) & 0xffffu) | ((uint32_t)(qb - 8192) << 16);
 }
-GS_HD uint32_t pack_sc08(int64_t acc) // (signed char)(short>>4) for I then Q, in the low 16 bits
+GS_HD uint32_t pack_sc08(int32_t ib, int32_t qb) // (signed char)(short>>4) for I then Q, in the low 16 bits
 {
-    const uint32_t i8 = (uint32_t)((acc_i_biased(acc) >> 4) - 512) & 0xffu;
-    const uint32_t q8 = (uint32_t)((acc_q_biased(acc) >> 4) - 512) & 0xffu;
-    return i8 | (q8 << 8);
+    return ((uint32_t)((ib >> 4) - 512) & 0xffu) | (((uint32_t)((qb >> 4) - 512) & 0xffu) << 8);
 }
-GS_HD uint32_t pack_sc01(int64_t acc) // 2 bits: (I>0)<<1 | (Q>0)
+GS_HD uint32_t pack_sc01(int32_t ib, int32_t qb) // 2 bits: (I>0)<<1 | (Q>0)
 {
-    return ((acc_i_biased(acc) > 8192) ? 2u : 0u) | ((acc_q_biased(acc) > 8192) ? 1u : 0u);
+    return ((ib > 8192) ? 2u : 0u) | ((qb > 8192) ? 1u : 0u);
 }
 
 // S consecutive samples of one thread -> their bytes at dst (16-byte aligned for SC16 / SC08,
@@ -337,21 +405,23 @@ GS_HD void store16(uint8_t *dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 #endif
 }
 
-template <int FMT, int S>
-GS_HD void store_run(uint8_t *dst, const int64_t (&acc)[S])
+template <class A, int FMT, int S>
+GS_HD void store_run(uint8_t *dst, const typename A::acc_t (&acc)[S])
 {
+#define GS_P16(j) pack_sc16(A::i_biased(acc[j]), A::q_biased(acc[j]))
+#define GS_P08(j) pack_sc08(A::i_biased(acc[j]), A::q_biased(acc[j]))
+#define GS_P01(j) pack_sc01(A::i_biased(acc[j]), A::q_biased(acc[j]))
     if (FMT == 16) {
 #pragma unroll
         for (int q = 0; q < S / 4; q++)
-            store16(dst + 16 * q, pack_sc16(acc[4 * q]), pack_sc16(acc[4 * q + 1]),
-                    pack_sc16(acc[4 * q + 2]), pack_sc16(acc[4 * q + 3]));
+            store16(dst + 16 * q, GS_P16(4 * q), GS_P16(4 * q + 1), GS_P16(4 * q + 2), GS_P16(4 * q + 3));
     } else if (FMT == 8) {
 #pragma unroll
         for (int q = 0; q < S / 8; q++) {
             uint32_t w[4];
 #pragma unroll
             for (int h = 0; h < 4; h++)
-                w[h] = pack_sc08(acc[8 * q + 2 * h]) | (pack_sc08(acc[8 * q + 2 * h + 1]) << 16);
+                w[h] = GS_P08(8 * q + 2 * h) | (GS_P08(8 * q + 2 * h + 1) << 16);
             store16(dst + 16 * q, w[0], w[1], w[2], w[3]);
         }
     } else {
@@ -362,8 +432,7 @@ GS_HD void store_run(uint8_t *dst, const int64_t (&acc)[S])
 #pragma unroll
             for (int b = 0; b < 4; b++) {
                 const int s0 = 16 * q + 4 * b;
-                const uint32_t byte = (pack_sc01(acc[s0]) << 6) | (pack_sc01(acc[s0 + 1]) << 4) |
-                                      (pack_sc01(acc[s0 + 2]) << 2) | pack_sc01(acc[s0 + 3]);
+                const uint32_t byte = (GS_P01(s0) << 6) | (GS_P01(s0 + 1) << 4) | (GS_P01(s0 + 2) << 2) | GS_P01(s0 + 3);
                 w |= byte << (8 * b);
             }
 #ifdef __CUDA_ARCH__
@@ -373,6 +442,9 @@ GS_HD void store_run(uint8_t *dst, const int64_t (&acc)[S])
 #endif
         }
     }
+#undef GS_P16
+#undef GS_P08
+#undef GS_P01
 }
 
 // =====================================================================================

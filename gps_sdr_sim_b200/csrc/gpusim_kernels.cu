@@ -63,9 +63,9 @@ constexpr int kK2Threads = 512;
 
 int synth_threads() { return kK2Threads; }
 
-// shared memory: [lut 512*32 i32][negw 33*33 u32, padded][x f64 [C][T]][phs u32 [C][T]][meta u32 [C][T]]
-constexpr size_t kSmemLut = (size_t)kLutEntries * kLutReplicas * sizeof(int32_t);
-constexpr size_t kSmemNegw = ((size_t)kCaPrns * kCaWords * sizeof(uint32_t) + 15) & ~(size_t)15;
+// shared memory: [carrier table 64 KB][negw 33*33 u32, padded][x f64 [C][T]][phs u32 [C][T]][meta u32 [C][T]]
+constexpr size_t kSmemLut = (size_t)kLutBytes;
+constexpr size_t kSmemNegw = ((size_t)(kCaPrns * kCaWords + 32) * sizeof(uint32_t) + 15) & ~(size_t)15; // + lane table
 
 size_t synth_smem_bytes(int max_active, int threads)
 {
@@ -74,27 +74,38 @@ size_t synth_smem_bytes(int max_active, int threads)
     return kSmemLut + kSmemNegw + (size_t)max_active * threads * 16;
 }
 
-template <int FMT, int S>
+template <class A, int FMT, int S>
 __global__ void __launch_bounds__(kK2Threads, 1) k2_synth(DeviceJob job)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    int32_t *lut = reinterpret_cast<int32_t *>(smem);
+    typedef typename A::tab_t tab_t;
+    typedef typename A::acc_t acc_t;
+    tab_t *lut = reinterpret_cast<tab_t *>(smem);
     uint32_t *negw = reinterpret_cast<uint32_t *>(smem + kSmemLut);
+    uint32_t *lane_tab = negw + kCaPrns * kCaWords;
     double *st_x = reinterpret_cast<double *>(smem + kSmemLut + kSmemNegw);
     uint32_t *st_phs = reinterpret_cast<uint32_t *>(st_x + (size_t)job.max_active * kK2Threads);
     uint32_t *st_meta = st_phs + (size_t)job.max_active * kK2Threads;
 
     const int tid = threadIdx.x;
-    // one replica of the packed carrier table per lane: entry i of lane l at word i*32+l,
-    // so lane l only ever touches bank l
-    for (int i = tid; i < kLutEntries * kLutReplicas; i += kK2Threads)
-        lut[i] = job.lut[i >> 5];
+    // replicated carrier table: entry i, replica r at byte i*128 + r*sizeof(tab_t); a lane always
+    // reads its own replica, so no lookup ever has a bank conflict
+    {
+        const tab_t *src = sizeof(tab_t) == 4 ? reinterpret_cast<const tab_t *>(job.lut_wide)
+                                              : reinterpret_cast<const tab_t *>(job.lut_f32);
+        constexpr int kPerEntry = 128 / (int)sizeof(tab_t);
+        for (int i = tid; i < kLutEntries * kPerEntry; i += kK2Threads)
+            lut[i] = src[i / kPerEntry];
+    }
     for (int i = tid; i < kCaPrns * kCaWords; i += kK2Threads)
         negw[i] = job.negw[i];
+    if (tid < 32)
+        lane_tab[tid] = (uint32_t)(tid & A::kLaneMask) << A::kLaneShift;
     __syncthreads();
 
-    const int lane = tid & 31;
-    const int32_t *mylut = lut + lane;
+    // this lane's replica offset, read back from shared memory so that ptxas cannot see its
+    // value range and keeps (x & 0xff80) | lane_off as ONE LOP3
+    const uint32_t lane_off = *reinterpret_cast<volatile uint32_t *>(lane_tab + (tid & 31));
 
     const long long total = (long long)job.n_epochs * job.kc;
     const long long gid = (long long)blockIdx.x * kK2Threads + tid;
@@ -127,10 +138,10 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_synth(DeviceJob job)
     uint8_t *outp = job.out + (size_t)e * job.epoch_bytes + (size_t)(n0 / 16) * bytes_per_16;
 
     for (int s0 = 0; s0 < nrun; s0 += S) {
-        int64_t acc[S];
+        acc_t acc[S];
 #pragma unroll
         for (int j = 0; j < S; j++)
-            acc[j] = kAccBias;
+            acc[j] = A::init();
 
         for (int k = 0; k < ncw; k++) {
             const bool act = k < nc;
@@ -152,17 +163,16 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_synth(DeviceJob job)
                 const uint32_t *nw = negw + (size_t)r.prn * kCaWords;
                 const uint32_t steps = (uint32_t)r.step << 7;
                 if (!any_wrap) {
-                    const int32_t g = data_sign(r.nav_bits, st.bitk) * r.gain * (1 << kAccShiftQ);
-                    synth_fast<S>(acc, st, r.d, steps, g, nw, mylut);
+                    synth_fast<A, S>(acc, st, r.d, steps, data_sign(r.nav_bits, st.bitk) * r.gain, nw, lut, lane_off);
                 } else {
-                    synth_wrap<S>(acc, st, r.d, steps, r.gain, r.nav_bits, nw, mylut);
+                    synth_wrap<A, S>(acc, st, r.d, steps, r.gain, r.nav_bits, nw, lut, lane_off);
                     st_meta[k * kK2Threads + tid] = (uint32_t)st.icode | ((uint32_t)st.bitk << 8);
                 }
                 st_x[k * kK2Threads + tid] = st.x;
                 st_phs[k * kK2Threads + tid] = st.phs;
             }
         }
-        store_run<FMT, S>(outp + (size_t)(s0 / 16) * bytes_per_16, acc);
+        store_run<A, FMT, S>(outp + (size_t)(s0 / 16) * bytes_per_16, acc);
     }
 }
 
@@ -221,17 +231,23 @@ __global__ void __launch_bounds__(128) k2_generic(DeviceJob job)
     }
 }
 
-template <int FMT, int S>
-static cudaError_t launch_tuned(const DeviceJob &job, cudaStream_t stream)
+template <class A, int FMT, int S>
+static cudaError_t launch_tuned_a(const DeviceJob &job, cudaStream_t stream)
 {
     const size_t smem = synth_smem_bytes(job.max_active, kK2Threads);
-    cudaError_t err = cudaFuncSetAttribute(k2_synth<FMT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = cudaFuncSetAttribute(k2_synth<A, FMT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess)
         return err;
     const long long total = (long long)job.n_epochs * job.kc;
     const int blocks = (int)((total + kK2Threads - 1) / kK2Threads);
-    k2_synth<FMT, S><<<blocks, kK2Threads, smem, stream>>>(job);
+    k2_synth<A, FMT, S><<<blocks, kK2Threads, smem, stream>>>(job);
     return cudaGetLastError();
+}
+
+template <int FMT, int S>
+static cudaError_t launch_tuned(const DeviceJob &job, cudaStream_t stream)
+{
+    return job.accum == 1 ? launch_tuned_a<AccF32x2, FMT, S>(job, stream) : launch_tuned_a<AccWide, FMT, S>(job, stream);
 }
 
 template <int FMT>

@@ -17,7 +17,8 @@ struct DeviceJob {
     const double *x0;        // [n_epochs][16] code_phase at epoch start
     double *ck_x;            // [n_epochs][16][kc] code phase at sample j*chunk
     uint16_t *ck_w;          // [n_epochs][16][kc] 1023-chip wraps before sample j*chunk
-    const int32_t *lut;      // [512] packed carrier table words (lut_word)
+    const int32_t *lut_wide; // [512] AccWide::table_entry(cos, sin)
+    const uint64_t *lut_f32; // [512] AccF32x2::table_entry(cos, sin)
     const int16_t *sin16;    // [512] plain tables for the generic kernel
     const int16_t *cos16;    // [512]
     const uint32_t *negw;    // [33][33] inverted C/A chips per PRN
@@ -30,6 +31,7 @@ struct DeviceJob {
     int32_t epoch_bytes;
     int32_t max_active;      // max nch over the range (sizes the per-thread state)
     int32_t force_wrap_path; // test hook: always run the wrap-checking loop
+    int32_t accum;           // 0 = AccWide (64-bit IMAD), 1 = AccF32x2 (FFMA2)
 };
 
 enum class ChainAlgo { Jump = 0, Replay = 1 };

@@ -16,15 +16,18 @@ namespace {
 
 struct Tables {
     std::vector<int32_t> lut;   // [512][32] replicated like the kernel's shared memory
+    std::vector<uint64_t> lut2; // [512][16]
     std::vector<int16_t> s16, c16;
     std::vector<uint32_t> negw; // [33][33]
-    Tables() : lut(512 * 32), s16(512), c16(512), negw(kCaPrns * kCaWords, 0xffffffffu)
+    Tables() : lut(512 * 32), lut2(512 * 16), s16(512), c16(512), negw(kCaPrns * kCaWords, 0xffffffffu)
     {
         int32_t s[512], c[512];
         carrier_lut(s, c);
         for (int i = 0; i < 512; i++) {
             for (int l = 0; l < 32; l++)
-                lut[i * 32 + l] = lut_word(c[i], s[i]);
+                lut[i * 32 + l] = AccWide::table_entry(c[i], s[i]);
+            for (int l = 0; l < 16; l++)
+                lut2[i * 16 + l] = AccF32x2::table_entry(c[i], s[i]);
             s16[i] = (int16_t)s[i];
             c16[i] = (int16_t)c[i];
         }
@@ -37,7 +40,11 @@ struct Tables {
     }
 };
 
-template <int FMT, int S>
+template <class A> const typename A::tab_t *table_of(const Tables &T);
+template <> const int32_t *table_of<AccWide>(const Tables &T) { return T.lut.data(); }
+template <> const uint64_t *table_of<AccF32x2>(const Tables &T) { return T.lut2.data(); }
+
+template <class A, int FMT, int S>
 void tuned_chunk(const Tables &T, const DevRow *rows, int nc, const double *ckx, const uint16_t *ckw, int kc,
                  int jc, int chunk, int N, int force_wrap, int lane, uint8_t *epoch_out)
 {
@@ -53,24 +60,24 @@ void tuned_chunk(const Tables &T, const DevRow *rows, int nc, const double *ckx,
     }
     const int bytes_per_16 = (FMT == 16) ? 64 : (FMT == 8) ? 32 : 4;
     uint8_t *outp = epoch_out + (size_t)(n0 / 16) * bytes_per_16;
-    const int32_t *mylut = T.lut.data() + lane;
+    const typename A::tab_t *lut = table_of<A>(T);
+    const uint32_t lane_off = (uint32_t)(lane & A::kLaneMask) << A::kLaneShift;
     for (int s0 = 0; s0 < nrun; s0 += S) {
-        int64_t acc[S];
+        typename A::acc_t acc[S];
         for (int j = 0; j < S; j++)
-            acc[j] = kAccBias;
+            acc[j] = A::init();
         for (int k = 0; k < nc; k++) {
             const DevRow &r = rows[k];
             const bool wrap = !(st[k].x + (double)(S + 1) * r.d < (double)kCaLen) || force_wrap;
             const uint32_t *nw = T.negw.data() + (size_t)r.prn * kCaWords;
             const uint32_t steps = (uint32_t)r.step << 7;
             if (!wrap) {
-                const int32_t g = data_sign(r.nav_bits, st[k].bitk) * r.gain * (1 << kAccShiftQ);
-                synth_fast<S>(acc, st[k], r.d, steps, g, nw, mylut);
+                synth_fast<A, S>(acc, st[k], r.d, steps, data_sign(r.nav_bits, st[k].bitk) * r.gain, nw, lut, lane_off);
             } else {
-                synth_wrap<S>(acc, st[k], r.d, steps, r.gain, r.nav_bits, nw, mylut);
+                synth_wrap<A, S>(acc, st[k], r.d, steps, r.gain, r.nav_bits, nw, lut, lane_off);
             }
         }
-        store_run<FMT, S>(outp + (size_t)(s0 / 16) * bytes_per_16, acc);
+        store_run<A, FMT, S>(outp + (size_t)(s0 / 16) * bytes_per_16, acc);
     }
 }
 
@@ -123,7 +130,7 @@ extern "C" {
 // kernel: 0 = tuned S=32, 1 = tuned S=16, 2 = generic.  Returns 0, or -1 if the table is outside
 // the selected kernel's documented ranges.
 int emu_generate(const gpusim_epoch_table *t, int N, double delt, int fmt, int chunk, int kernel,
-                 int force_wrap, int chain_replay, uint8_t *out)
+                 int force_wrap, int chain_replay, int accum, uint8_t *out)
 {
     static const Tables T;
     const size_t eb = fmt == 1 ? (size_t)(N / 4) : fmt == 8 ? (size_t)2 * N : (size_t)4 * N;
@@ -168,7 +175,11 @@ int emu_generate(const gpusim_epoch_table *t, int N, double delt, int fmt, int c
         uint8_t *eo = out + (size_t)e * eb;
         for (int jc = 0; jc < kc; jc++) {
             const int lane = jc & 31;
-#define EMU_TUNED(F, S) tuned_chunk<F, S>(T, rows, nc, ckx.data(), ckw.data(), kc, jc, chunk, N, force_wrap, lane, eo)
+#define EMU_TUNED(F, S)                                                                                          \
+    do {                                                                                                         \
+        if (accum == 1) tuned_chunk<AccF32x2, F, S>(T, rows, nc, ckx.data(), ckw.data(), kc, jc, chunk, N, force_wrap, lane, eo); \
+        else tuned_chunk<AccWide, F, S>(T, rows, nc, ckx.data(), ckw.data(), kc, jc, chunk, N, force_wrap, lane, eo);            \
+    } while (0)
             if (kernel == 0) {
                 if (fmt == 16) EMU_TUNED(16, 32); else if (fmt == 8) EMU_TUNED(8, 32); else EMU_TUNED(1, 32);
             } else if (kernel == 1) {

@@ -33,7 +33,7 @@ def lib() -> ctypes.CDLL:
         _lib = ctypes.CDLL(build())
         _lib.emu_generate.restype = ctypes.c_int
         _lib.emu_generate.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int,
-                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         _lib.emu_code_chain.restype = None
         _lib.emu_code_chain.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_void_p]
@@ -41,11 +41,11 @@ def lib() -> ctypes.CDLL:
 
 
 def generate(table, chunk: int = 512, kernel: int = TUNED32, force_wrap: bool = False,
-             chain_replay: bool = False) -> np.ndarray:
+             chain_replay: bool = False, accum: int = 0) -> np.ndarray:
     out = np.zeros(table.n_epochs * table.epoch_bytes, dtype=np.uint8)
     c = table.as_c()
     rc = lib().emu_generate(ctypes.addressof(c), table.samples_per_epoch, table.delt, table.data_format, chunk,
-                            kernel, int(force_wrap), int(chain_replay), out.ctypes.data)
+                            kernel, int(force_wrap), int(chain_replay), accum, out.ctypes.data)
     if rc != 0:
         raise ValueError("table outside the selected kernel's ranges")
     return out

@@ -53,6 +53,8 @@ struct gpusim_ctx {
     // checkpoints, sized for min_chunk
     double *d_ck_x = nullptr;
     uint16_t *d_ck_w = nullptr;
+    unsigned int *d_work = nullptr;
+    int sm_count = 148;
     int min_chunk = 128;
 
     // output
@@ -90,14 +92,15 @@ int fail(gpusim_ctx *ctx, int status, const char *fmt, ...)
 
 int kc_for(int n_samples, int chunk) { return (n_samples + chunk - 1) / chunk; }
 
-// samples per thread chunk: as large as still gives ~2 waves of 512-thread blocks on 148 SMs
+// samples per thread chunk.  K2 runs one persistent 512-thread block per SM whose warps claim units
+// of 32 chunks; pick the largest chunk that still leaves every warp >= 16 units to balance with.
 int pick_chunk(const gpusim_ctx *ctx, int n_epochs)
 {
     if (ctx->opt_chunk > 0)
         return std::max(ctx->min_chunk, (ctx->opt_chunk + 31) / 32 * 32);
-    const long long want = 2LL * 148 * synth_threads();
+    const long long want = 16LL * 32 * ctx->sm_count * (synth_threads() / 32);
     int chunk = 1024;
-    while (chunk > ctx->min_chunk && (long long)n_epochs * kc_for(ctx->cfg.samples_per_epoch, chunk) < want)
+    while (chunk > ctx->min_chunk && chunk > 128 && (long long)n_epochs * kc_for(ctx->cfg.samples_per_epoch, chunk) < want)
         chunk /= 2;
     return std::max(chunk, ctx->min_chunk);
 }
@@ -135,6 +138,8 @@ int launch_range(gpusim_ctx *ctx, int first, int n, uint8_t *out_dev, cudaStream
     job.cos16 = ctx->d_cos16;
     job.negw = ctx->d_negw;
     job.out = out_dev;
+    job.work_counter = ctx->d_work;
+    job.sm_count = ctx->sm_count;
     job.n_epochs = n;
     job.n_samples = ctx->cfg.samples_per_epoch;
     job.chunk = pick_chunk(ctx, n);
@@ -209,7 +214,7 @@ void gpusim_destroy(gpusim_ctx *ctx)
     if (ctx->s_copy) cudaStreamSynchronize(ctx->s_copy);
     cudaFree(ctx->d_lut); cudaFree(ctx->d_lut_f32); cudaFree(ctx->d_sin16); cudaFree(ctx->d_cos16); cudaFree(ctx->d_negw);
     cudaFree(ctx->d_rows); cudaFree(ctx->d_nch); cudaFree(ctx->d_x0);
-    cudaFree(ctx->d_ck_x); cudaFree(ctx->d_ck_w); cudaFree(ctx->d_out);
+    cudaFree(ctx->d_ck_x); cudaFree(ctx->d_ck_w); cudaFree(ctx->d_work); cudaFree(ctx->d_out);
     cudaFreeHost(ctx->h_rows); cudaFreeHost(ctx->h_nch); cudaFreeHost(ctx->h_x0);
     cudaFreeHost(ctx->h_stage[0]); cudaFreeHost(ctx->h_stage[1]);
     for (cudaEvent_t ev : {ctx->ev_t0, ctx->ev_t1, ctx->ev_t2, ctx->ev_done[0], ctx->ev_done[1],
@@ -317,6 +322,9 @@ int gpusim_create(const gpusim_config *cfg, gpusim_ctx **out_ctx)
     const size_t cks = rows * (size_t)kc_for(N, ctx->min_chunk);
     GS_CREATE(cudaMalloc(&ctx->d_ck_x, cks * sizeof(double)));
     GS_CREATE(cudaMalloc(&ctx->d_ck_w, cks * sizeof(uint16_t)));
+    GS_CREATE(cudaMalloc(&ctx->d_work, 64));
+    GS_CREATE(cudaMemset(ctx->d_work, 0, 64));
+    GS_CREATE(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
 #undef GS_CREATE
 
     *out_ctx = ctx;

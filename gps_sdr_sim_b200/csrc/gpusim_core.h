@@ -32,7 +32,7 @@ constexpr int kMaxChan = 16;
 constexpr int kCaLen = 1023;
 constexpr int kLutEntries = 512;
 constexpr int kLutBytes = 512 * 128;  // replicated carrier table: 512 entries, 128 bytes apart
-constexpr int kCaWords = 33;         // per PRN, see gpusim_tables.h
+constexpr int kCaWords = 35;         // per PRN, see gpusim_tables.h
 constexpr int kCaPrns = 33;          // index by prn 0..32 (0 unused)
 
 // ---- exact IEEE-754 double steps (never contracted into FMA) -----------------------
@@ -82,6 +82,17 @@ GS_HD uint32_t chips_since(double x, double magic)
     return (uint32_t)__double2loint(__dadd_rd(x, magic));
 #else
     int c0 = (int)(4503599627370496.0 - magic);
+    return (uint32_t)((int)x - c0);
+#endif
+}
+// Same with magic = 1.5*2^52 - c0: also valid when x < c0 (after the 1023-chip wrap), the
+// result is then floor(x) - c0 as a two's complement 32-bit number.
+GS_HD uint32_t chips_since_signed(double x, double magic15)
+{
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__double2loint(__dadd_rd(x, magic15));
+#else
+    int c0 = (int)(6755399441055744.0 - magic15);
     return (uint32_t)((int)x - c0);
 #endif
 }
@@ -211,22 +222,33 @@ struct AccF32x2 {
 //
 // emit(j, x, wraps) is called for sample indices j*every, j = 0 .. ceil(n_total/every)-1.
 // =====================================================================================
+// floor(room / q) for room < 2^53, 2^32 <= q: a float estimate plus one exact correction
+// (a 64-bit division costs several hundred dependent cycles, and this chain is latency bound)
+GS_HD uint64_t div_small_quotient(uint64_t room, uint64_t q)
+{
+    const float est = (float)room / (float)q;
+    if (!(est < 1048576.0f))
+        return room / q; // never on real tables: more than 2^20 steps inside one binade
+    uint64_t k = (uint64_t)est;
+    const uint64_t prod = k * q;
+    if (prod > room)
+        k--;
+    else if (room - prod >= q)
+        k++;
+    return k;
+}
+
 template <class Emit>
 GS_HD void code_chain(double x, const double d, const int n_total, const int every, Emit emit)
 {
     const uint64_t db = dbits(d);
     const int ed = (int)((db >> 52) & 0x7ff) - 1023;
     const uint64_t dm = (db & 0xfffffffffffffull) | (1ull << 52);
-    const int last = ((n_total - 1) / every) * every;
-    int n = 0, next = 0, j = 0, wraps = 0;
+    const int last = ((n_total - 1) / every) * every; // sample index of the last checkpoint
+    int n = 0, next = every, j = 1, wraps = 0;
 
-    for (;;) {
-        if (n == next) {
-            emit(j++, x, wraps);
-            if (n >= last)
-                break;
-            next += every;
-        }
+    emit(0, x, 0);
+    while (n < last) {
         const uint64_t xb = dbits(x);
         const int ex = (int)((xb >> 52) & 0x7ff) - 1023;
         const int shift = ex - ed;
@@ -246,18 +268,21 @@ GS_HD void code_chain(double x, const double d, const int n_total, const int eve
             if (ok) {
                 // stay strictly inside the binade and strictly below the 1023 wrap
                 const uint64_t lim = (ex == 9) ? ((uint64_t)kCaLen << 43) : (1ull << 53);
-                const uint64_t room = lim - 1 - m;
-                uint64_t k = room / q;
-                const uint64_t to_next = (uint64_t)(next - n);
-                if (k > to_next)
-                    k = to_next;
-                if (k > 0) {
-                    m += k * q;
-                    x = dfrombits(((uint64_t)(ex + 1023) << 52) | (m & 0xfffffffffffffull));
-                    n += (int)k;
-                    if (n == next)
-                        continue;
+                uint64_t k = div_small_quotient(lim - 1 - m, q);
+                if (k > (uint64_t)(last - n))
+                    k = (uint64_t)(last - n);
+                const uint64_t ebits = (uint64_t)(ex + 1023) << 52;
+                // checkpoints that fall inside the jump
+                while ((uint64_t)(next - n) <= k) {
+                    const uint64_t mc = m + (uint64_t)(next - n) * q;
+                    emit(j++, dfrombits(ebits | (mc & 0xfffffffffffffull)), wraps);
+                    next += every;
                 }
+                m += k * q;
+                n += (int)k;
+                x = dfrombits(ebits | (m & 0xfffffffffffffull));
+                if (n >= last)
+                    break;
             }
         }
         // one genuine step of gpssim.c:2212-2218
@@ -267,6 +292,10 @@ GS_HD void code_chain(double x, const double d, const int n_total, const int eve
             wraps++;
         }
         n++;
+        if (n == next) {
+            emit(j++, x, wraps);
+            next += every;
+        }
     }
 }
 
@@ -345,7 +374,10 @@ GS_HD void synth_fast(typename A::acc_t (&acc)[S], ChanState &st, const double d
 }
 
 // Same samples, but the 1023-chip wrap (and with it the icode / data-bit walk of
-// gpssim.c:2214-2238) may happen inside the run.
+// gpssim.c:2214-2238) may happen inside the run - at most once, a run is far shorter than a
+// code period.  Branch-free: the chip window comes from a code table that continues past chip
+// 1022 with chips 0,1,.. again, so after the wrap the advance is simply counted 1023 chips
+// further; the data bit (and with it the signed gain) switches to a value prepared up front.
 template <class A, int S>
 GS_HD void synth_wrap(typename A::acc_t (&acc)[S], ChanState &st, const double d, const uint32_t steps,
                       const int32_t gain, const uint32_t nav_bits, const uint32_t *negw,
@@ -353,27 +385,28 @@ GS_HD void synth_wrap(typename A::acc_t (&acc)[S], ChanState &st, const double d
 {
     double x = st.x;
     uint32_t phs = st.phs;
-    int c0 = (int)x;
-    uint32_t win = funnel_l(negw[(c0 >> 5) + 1], negw[c0 >> 5], (uint32_t)c0 & 31u);
-    double magic = 4503599627370496.0 - (double)c0;
+    const int c0 = (int)x;
+    const uint32_t win = funnel_l(negw[(c0 >> 5) + 1], negw[c0 >> 5], (uint32_t)c0 & 31u);
+    const double magic = 6755399441055744.0 - (double)c0; // 1.5 * 2^52 - c0
+    const int bit_after = st.bitk + (st.icode == 19 ? 1 : 0);
     typename A::gain_t g = A::make_gain(data_sign(nav_bits, st.bitk) * gain);
+    const typename A::gain_t g_after = A::make_gain(data_sign(nav_bits, bit_after) * gain);
+    uint32_t wrap_off = 0;
 #pragma unroll
     for (int j = 0; j < S; j++) {
-        const uint32_t adv = chips_since(x, magic);
+        const uint32_t adv = chips_since_signed(x, magic) + wrap_off;
         const uint32_t e = phs ^ ((win << adv) & 0x80000000u);
         A::mad(acc[j], lut_at<A>(lut, e, lane_off), g);
         x = dadd(x, d);
         phs += steps;
-        if (x >= (double)kCaLen) {
-            x = dadd(x, -(double)kCaLen);
-            if (++st.icode >= 20) {
-                st.icode = 0;
-                st.bitk++;
-                g = A::make_gain(data_sign(nav_bits, st.bitk) * gain);
-            }
-            win = negw[0];
-            magic = 4503599627370496.0;
-        }
+        const bool wrapped = x >= (double)kCaLen;
+        x = wrapped ? dadd(x, -(double)kCaLen) : x;
+        wrap_off = wrapped ? (uint32_t)kCaLen : wrap_off;
+        g = wrapped ? g_after : g;
+    }
+    if (wrap_off) {
+        st.icode = st.icode == 19 ? 0 : st.icode + 1;
+        st.bitk = bit_after;
     }
     st.x = x;
     st.phs = phs;

@@ -12,6 +12,8 @@
 // instruction issue (INT / FP64 / LDS per sample and channel) below an HBM-write roof.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "gpusim_kernels.h"
 
 namespace gpusim {
@@ -23,6 +25,8 @@ template <bool kReplay>
 __global__ void __launch_bounds__(128) k1_chain(DeviceJob job)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx == 0)
+        *job.work_counter = 0; // K2 of the same job runs after this kernel on the same stream
     const int e = idx / kMaxChan;
     const int k = idx % kMaxChan;
     if (e >= job.n_epochs || k >= job.nch[e])
@@ -107,72 +111,89 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_synth(DeviceJob job)
     // value range and keeps (x & 0xff80) | lane_off as ONE LOP3
     const uint32_t lane_off = *reinterpret_cast<volatile uint32_t *>(lane_tab + (tid & 31));
 
+    // Persistent warps: every warp repeatedly claims a unit of 32 consecutive chunks (one per lane).
+    // No block-level synchronisation after the tables are built, so a warp that runs the longer
+    // wrap-checking loop never holds up the others, and the tail of the grid is one unit long.
     const long long total = (long long)job.n_epochs * job.kc;
-    const long long gid = (long long)blockIdx.x * kK2Threads + tid;
-    const bool valid = gid < total;
-    const unsigned mask = __ballot_sync(0xffffffffu, valid);
-    if (!valid)
-        return;
-
-    const int e = (int)(gid / job.kc);
-    const int jc = (int)(gid - (long long)e * job.kc);
-    const int n0 = jc * job.chunk;
-    const int nrun = min(job.chunk, job.n_samples - n0);
-    const DevRow *rows = job.rows + (size_t)e * kMaxChan;
-    const int nc = job.nch[e];
-
-    // chunk-start state of every channel
-    for (int k = 0; k < nc; k++) {
-        const size_t ck = ((size_t)e * kMaxChan + k) * job.kc + jc;
-        const DevRow r = rows[k];
-        const int ic = (int)r.icode0 + (int)job.ck_w[ck];
-        st_x[k * kK2Threads + tid] = job.ck_x[ck];
-        st_phs[k * kK2Threads + tid] = (r.ph0 + (uint32_t)n0 * (uint32_t)r.step) << 7;
-        st_meta[k * kK2Threads + tid] = (uint32_t)(ic % 20) | ((uint32_t)(ic / 20) << 8);
-    }
-
-    // warp-wide channel count so that every lane takes part in every vote
-    const int ncw = (int)__reduce_max_sync(mask, (unsigned)nc);
-
+    const int lane = tid & 31;
     const int bytes_per_16 = (FMT == 16) ? 64 : (FMT == 8) ? 32 : 4;
-    uint8_t *outp = job.out + (size_t)e * job.epoch_bytes + (size_t)(n0 / 16) * bytes_per_16;
 
-    for (int s0 = 0; s0 < nrun; s0 += S) {
-        acc_t acc[S];
-#pragma unroll
-        for (int j = 0; j < S; j++)
-            acc[j] = A::init();
+    for (;;) {
+        unsigned int unit = 0;
+        if (lane == 0)
+            unit = atomicAdd(job.work_counter, 1u);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        const long long gid = (long long)unit * 32 + lane;
+        if ((long long)unit * 32 >= total)
+            break;
+        const bool valid = gid < total;
+        const unsigned mask = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const int e = (int)(gid / job.kc);
+            const int jc = (int)(gid - (long long)e * job.kc);
+            const int n0 = jc * job.chunk;
+            const int nrun = min(job.chunk, job.n_samples - n0);
+            const DevRow *rows = job.rows + (size_t)e * kMaxChan;
+            const int nc = job.nch[e];
 
-        for (int k = 0; k < ncw; k++) {
-            const bool act = k < nc;
-            ChanState st;
-            DevRow r;
-            bool wrap = false;
-            if (act) {
-                r = rows[k];
-                st.x = st_x[k * kK2Threads + tid];
-                st.phs = st_phs[k * kK2Threads + tid];
-                const uint32_t meta = st_meta[k * kK2Threads + tid];
-                st.icode = (int)(meta & 0xffu);
-                st.bitk = (int)(meta >> 8);
-                // conservative: a whole extra step of margin over the S rounded adds
-                wrap = !(st.x + (double)(S + 1) * r.d < (double)kCaLen) || job.force_wrap_path;
+            // chunk-start state of every channel
+            for (int k = 0; k < nc; k++) {
+                const size_t ck = ((size_t)e * kMaxChan + k) * job.kc + jc;
+                const DevRow r = rows[k];
+                const int ic = (int)r.icode0 + (int)job.ck_w[ck];
+                st_x[k * kK2Threads + tid] = job.ck_x[ck];
+                st_phs[k * kK2Threads + tid] = (r.ph0 + (uint32_t)n0 * (uint32_t)r.step) << 7;
+                st_meta[k * kK2Threads + tid] = (uint32_t)(ic % 20) | ((uint32_t)(ic / 20) << 8);
             }
-            const bool any_wrap = __any_sync(mask, wrap);
-            if (act) {
-                const uint32_t *nw = negw + (size_t)r.prn * kCaWords;
-                const uint32_t steps = (uint32_t)r.step << 7;
-                if (!any_wrap) {
-                    synth_fast<A, S>(acc, st, r.d, steps, data_sign(r.nav_bits, st.bitk) * r.gain, nw, lut, lane_off);
-                } else {
-                    synth_wrap<A, S>(acc, st, r.d, steps, r.gain, r.nav_bits, nw, lut, lane_off);
-                    st_meta[k * kK2Threads + tid] = (uint32_t)st.icode | ((uint32_t)st.bitk << 8);
+
+            // warp-wide channel and sample counts: every participating lane runs the same number of
+            // loop iterations and takes part in every vote (the last chunk of an epoch is shorter,
+            // epochs may have different numbers of satellites)
+            const int ncw = (int)__reduce_max_sync(mask, (unsigned)nc);
+            const int nrun_w = (int)__reduce_max_sync(mask, (unsigned)nrun);
+            uint8_t *outp = job.out + (size_t)e * job.epoch_bytes + (size_t)(n0 / 16) * bytes_per_16;
+
+            for (int s0 = 0; s0 < nrun_w; s0 += S) {
+                const bool run_live = s0 < nrun;
+                acc_t acc[S];
+#pragma unroll
+                for (int j = 0; j < S; j++)
+                    acc[j] = A::init();
+
+                for (int k = 0; k < ncw; k++) {
+                    const bool act = run_live && k < nc;
+                    ChanState st;
+                    DevRow r;
+                    bool wrap = false;
+                    if (act) {
+                        r = rows[k];
+                        st.x = st_x[k * kK2Threads + tid];
+                        st.phs = st_phs[k * kK2Threads + tid];
+                        const uint32_t meta = st_meta[k * kK2Threads + tid];
+                        st.icode = (int)(meta & 0xffu);
+                        st.bitk = (int)(meta >> 8);
+                        // conservative: a whole extra step of margin over the S rounded adds
+                        wrap = !(st.x + (double)(S + 1) * r.d < (double)kCaLen) || job.force_wrap_path;
+                    }
+                    const bool any_wrap = __any_sync(mask, wrap);
+                    if (act) {
+                        const uint32_t *nw = negw + (size_t)r.prn * kCaWords;
+                        const uint32_t steps = (uint32_t)r.step << 7;
+                        if (!any_wrap) {
+                            synth_fast<A, S>(acc, st, r.d, steps, data_sign(r.nav_bits, st.bitk) * r.gain, nw, lut, lane_off);
+                        } else {
+                            synth_wrap<A, S>(acc, st, r.d, steps, r.gain, r.nav_bits, nw, lut, lane_off);
+                            st_meta[k * kK2Threads + tid] = (uint32_t)st.icode | ((uint32_t)st.bitk << 8);
+                        }
+                        st_x[k * kK2Threads + tid] = st.x;
+                        st_phs[k * kK2Threads + tid] = st.phs;
+                    }
                 }
-                st_x[k * kK2Threads + tid] = st.x;
-                st_phs[k * kK2Threads + tid] = st.phs;
+                if (run_live)
+                    store_run<A, FMT, S>(outp + (size_t)(s0 / 16) * bytes_per_16, acc);
             }
         }
-        store_run<A, FMT, S>(outp + (size_t)(s0 / 16) * bytes_per_16, acc);
+        __syncwarp();
     }
 }
 
@@ -238,8 +259,9 @@ static cudaError_t launch_tuned_a(const DeviceJob &job, cudaStream_t stream)
     cudaError_t err = cudaFuncSetAttribute(k2_synth<A, FMT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess)
         return err;
-    const long long total = (long long)job.n_epochs * job.kc;
-    const int blocks = (int)((total + kK2Threads - 1) / kK2Threads);
+    const long long units = ((long long)job.n_epochs * job.kc + 31) / 32;
+    const long long warps_per_block = kK2Threads / 32;
+    const int blocks = (int)std::min<long long>(std::max(1, job.sm_count), (units + warps_per_block - 1) / warps_per_block);
     k2_synth<A, FMT, S><<<blocks, kK2Threads, smem, stream>>>(job);
     return cudaGetLastError();
 }

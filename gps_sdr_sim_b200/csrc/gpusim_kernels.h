@@ -23,6 +23,7 @@ struct DeviceJob {
     const int16_t *cos16;    // [512]
     const uint32_t *negw;    // [33][33] inverted C/A chips per PRN
     uint8_t *out;            // n_epochs * epoch_bytes
+    unsigned int *work_counter; // zeroed by K1, handed out by K2's warps (32 chunks per unit)
     int32_t n_epochs;
     int32_t n_samples;       // samples per epoch
     int32_t chunk;           // samples per thread chunk (multiple of 32)
@@ -32,6 +33,7 @@ struct DeviceJob {
     int32_t max_active;      // max nch over the range (sizes the per-thread state)
     int32_t force_wrap_path; // test hook: always run the wrap-checking loop
     int32_t accum;           // 0 = AccWide (64-bit IMAD), 1 = AccF32x2 (FFMA2)
+    int32_t sm_count;        // persistent K2 grid: one 512-thread block per SM
 };
 
 enum class ChainAlgo { Jump = 0, Replay = 1 };

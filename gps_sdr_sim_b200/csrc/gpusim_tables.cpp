@@ -84,17 +84,17 @@ int ca_code(int prn, uint8_t *chips)
     return 0;
 }
 
-// 33 words per PRN: chip k at word k>>5, bit 31-(k&31); chips >= 1023 read 0.
-void ca_words(int prn, uint32_t *words33)
+// 35 words per PRN: chip k (k < 1023+64, taken modulo 1023) at word k>>5, bit 31-(k&31).
+void ca_words(int prn, uint32_t *words35)
 {
     uint8_t chips[GPUSIM_CA_SEQ_LEN];
     for (int w = 0; w < kCaWordsPerPrn; w++)
-        words33[w] = 0;
+        words35[w] = 0;
     if (ca_code(prn, chips) != 0)
         return;
-    for (int k = 0; k < GPUSIM_CA_SEQ_LEN; k++)
-        if (chips[k])
-            words33[k >> 5] |= 0x80000000u >> (k & 31);
+    for (int k = 0; k < GPUSIM_CA_SEQ_LEN + 64; k++)
+        if (chips[k % GPUSIM_CA_SEQ_LEN])
+            words35[k >> 5] |= 0x80000000u >> (k & 31);
 }
 
 } // namespace gpusim

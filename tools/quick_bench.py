@@ -17,7 +17,7 @@ for fmt in (16, 8, 1):
     t = gs.synthetic_table(E, N, 13, fmt)
     out = torch.empty(t.n_epochs * t.epoch_bytes, dtype=torch.uint8, device="cuda")
     for accum in (0, 1):
-        for chunk in (0, 256, 512, 1024, 2048):
+        for chunk in (0, 128, 256, 512, 1024):
             for slow in (0, 1):
                 if slow and chunk:
                     continue

@@ -62,7 +62,7 @@ struct gpusim_ctx {
     uint8_t *h_stage[2] = {nullptr, nullptr};
 
     // options
-    int opt_chunk = 0, opt_force_generic = 0, opt_force_slow = 0, opt_chain_replay = 0, opt_accum = 0;
+    int opt_chunk = 0, opt_force_generic = 0, opt_force_slow = 0, opt_chain_replay = 0, opt_accum = 1, opt_layout = 0;
 
     gpusim_timing timing{};
 };
@@ -142,20 +142,48 @@ int launch_range(gpusim_ctx *ctx, int first, int n, uint8_t *out_dev, cudaStream
     job.sm_count = ctx->sm_count;
     job.n_epochs = n;
     job.n_samples = ctx->cfg.samples_per_epoch;
-    job.chunk = pick_chunk(ctx, n);
-    job.kc = kc_for(job.n_samples, job.chunk);
-    job.fmt = ctx->cfg.data_format;
-    job.epoch_bytes = (int32_t)ctx->epoch_bytes;
-    job.max_active = 1;
-    for (int e = first; e < first + n; e++)
-        job.max_active = std::max<int>(job.max_active, ctx->h_nch[e]);
-    job.force_wrap_path = ctx->opt_force_slow;
 
     SynthKernel which = SynthKernel::Tuned32;
     if (ctx->opt_force_generic || ctx->needs_generic || (job.n_samples % 32) != 0 || ctx->d_max >= 2.0)
         which = SynthKernel::Generic;
     else if (ctx->d_max > 0.9999)
         which = SynthKernel::Tuned16;
+
+    // Work layout of the tuned kernel.  Aligned: an epoch is 100 nominal C/A code periods; a chunk is
+    // 1/q of a period and the 32 lanes of a unit take the same slot of 32 consecutive periods, so
+    // the 1023-chip wrap reaches all lanes of a warp in the same run (see k2_synth).  Needs the
+    // period to be a whole number of samples and the chunk a multiple of 8 samples; otherwise
+    // (or with option layout=1) chunks are a power of two and units are 32 consecutive chunks.
+    job.ppe = 0;
+    job.q = 0;
+    job.chunk = pick_chunk(ctx, n);
+    const long long want_units = 8LL * ctx->sm_count * (synth_threads() / 32);
+    if (which != SynthKernel::Generic && ctx->opt_layout != 1 && job.n_samples % 100 == 0) {
+        const int period = job.n_samples / 100;
+        const int floor_chunk = std::max(ctx->min_chunk, 64);
+        int best_q = 0;
+        for (int q = 1; q <= period; q++) {
+            if (period % q != 0 || (period / q) % 8 != 0 || period / q < floor_chunk || period / q > 4096)
+                continue;
+            best_q = q; // smallest q (largest chunk) with enough units; else the largest admissible q
+            if (((long long)n * 100 + 31) / 32 * q >= want_units)
+                break;
+        }
+        if (best_q > 0) {
+            job.ppe = 100;
+            job.q = best_q;
+            job.chunk = period / best_q;
+        }
+    }
+    job.kc = kc_for(job.n_samples, job.chunk);
+    job.n_units = job.ppe > 0 ? (int32_t)((((long long)n * job.ppe + 31) / 32) * job.q)
+                              : (int32_t)(((long long)n * job.kc + 31) / 32);
+    job.fmt = ctx->cfg.data_format;
+    job.epoch_bytes = (int32_t)ctx->epoch_bytes;
+    job.max_active = 1;
+    for (int e = first; e < first + n; e++)
+        job.max_active = std::max<int>(job.max_active, ctx->h_nch[e]);
+    job.force_wrap_path = ctx->opt_force_slow;
 
     if (timed)
         GS_CUDA(ctx, cudaEventRecord(ctx->ev_t0, stream));
@@ -340,6 +368,7 @@ int gpusim_set_option(gpusim_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "force_slow")) ctx->opt_force_slow = (int)value;
     else if (!strcmp(key, "chain_replay")) ctx->opt_chain_replay = (int)value;
     else if (!strcmp(key, "accum")) ctx->opt_accum = (int)value;
+    else if (!strcmp(key, "layout")) ctx->opt_layout = (int)value;
     else return fail(ctx, GPUSIM_ERR_ARG, "unknown option '%s'", key);
     return GPUSIM_OK;
 }
@@ -373,16 +402,20 @@ int gpusim_upload_table(gpusim_ctx *ctx, const gpusim_epoch_table *t)
                 return fail(ctx, GPUSIM_ERR_ARG, "epoch %d slot %d: code_phase %.17g, f_code*delt %.17g or icode %d outside the reference's invariants", e, i, x0, (double)d, t->icode[r]);
             DevRow &o = ctx->h_rows[(size_t)e * kMaxChan + nc];
             o.d = d;
-            o.ph0 = t->carr_phase[r];
-            o.step = t->carr_phasestep[r];
+            o.steps = (int32_t)((uint32_t)t->carr_phasestep[r] << 7);
+            o.cthr = wrap_threshold(d);
+            o.prn = (uint8_t)t->prn[r];
+            o.ph0s = t->carr_phase[r] << 7;
             o.gain = t->gain[r];
             o.nav_bits = t->nav_bits[r];
-            o.prn = (uint16_t)t->prn[r];
             o.icode0 = (uint16_t)t->icode[r];
             o.flags = 0;
             if (o.gain < 0 || o.gain > kTunedMaxGain) {
                 o.flags |= kRowNeedsGeneric;
+                o.gain8 = 0;
                 ctx->needs_generic = true;
+            } else {
+                o.gain8 = (uint8_t)o.gain;
             }
             ctx->d_max = std::max(ctx->d_max, (double)d);
             ctx->h_x0[(size_t)e * kMaxChan + nc] = x0;

@@ -116,17 +116,31 @@ GS_HD int64_t mad_wide(int32_t a, int32_t b, int64_t c)
 }
 
 // ---- device-side row: one (epoch, active channel), 32 bytes -------------------------
+// The first 16 bytes are all the tuned kernel reads per run of samples; the second half is
+// needed once per chunk, in the wrap path and by the generic kernel.  The carrier phase is
+// kept shifted left by 7 (only bits 16..24 of carr_phase are ever used, gpssim.c:2202), so
+// the table index is the top 9 bits.
 struct alignas(16) DevRow {
     double d;          // RN(f_code*delt): the addend of gpssim.c:2212
-    uint32_t ph0;      // carr_phase at epoch start                     (INT mode)
-    int32_t step;      // carr_phasestep, gpssim.c:2176
+    int32_t steps;     // carr_phasestep << 7 (gpssim.c:2176)
+    uint16_t cthr;     // a run starting at floor(code_phase) >= cthr may reach the 1023-chip wrap
+    uint8_t prn;
+    uint8_t gain8;     // gain[i] when it is 0..255 (tuned kernels)
+    uint32_t ph0s;     // carr_phase at epoch start, << 7
     int32_t gain;      // gain[i], gpssim.c:2186
     uint32_t nav_bits; // next 32 data bits, MSB first
-    uint16_t prn;
     uint16_t icode0;   // chan[i].icode at epoch start
-    uint32_t flags;    // bit0: outside the tuned kernel's ranges
+    uint16_t flags;    // bit0: outside the tuned kernel's ranges
 };
 static_assert(sizeof(DevRow) == 32, "DevRow layout");
+
+// floor(code_phase) from which a run of up to 32 samples might wrap: 32 adds of d plus a whole
+// chip of margin over the rounding of the chain
+GS_HD uint16_t wrap_threshold(double d)
+{
+    const double t = 1022.0 - 33.0 * d;
+    return t <= 0.0 ? (uint16_t)0 : (uint16_t)(int)t;
+}
 
 constexpr uint32_t kRowNeedsGeneric = 1u;
 constexpr int kTunedMaxGain = 255; // 16 ch * 250 * 255 + 64 < 2^20: the accumulator fields below hold it
@@ -349,6 +363,14 @@ struct ChanState {
     int32_t icode; // 0..19
     int32_t bitk;  // data bits consumed since the row
 };
+// icode | bitk << 8 | (dataBit * gain) << 16: the per-thread, per-channel word kept next to x and phs
+GS_HD uint32_t pack_meta(int icode, int bitk, int signed_gain)
+{
+    return (uint32_t)icode | ((uint32_t)bitk << 8) | ((uint32_t)signed_gain << 16);
+}
+GS_HD int meta_icode(uint32_t m) { return (int)(m & 0xffu); }
+GS_HD int meta_bitk(uint32_t m) { return (int)((m >> 8) & 0xffu); }
+GS_HD int meta_sgain(uint32_t m) { return (int)(int32_t)m >> 16; }
 
 template <class A, int S>
 GS_HD void synth_fast(typename A::acc_t (&acc)[S], ChanState &st, const double d, const uint32_t steps,
@@ -427,7 +449,7 @@ GS_HD uint32_t pack_sc01(int32_t ib, int32_t qb) // 2 bits: (I>0)<<1 | (Q>0)
 }
 
 // S consecutive samples of one thread -> their bytes at dst (16-byte aligned for SC16 / SC08,
-// 4-byte aligned for SC01).  16-byte vector stores.
+// 2-byte aligned for SC01).  S is a multiple of 8.
 GS_HD void store16(uint8_t *dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 {
 #ifdef __CUDA_ARCH__
@@ -458,20 +480,22 @@ GS_HD void store_run(uint8_t *dst, const typename A::acc_t (&acc)[S])
             store16(dst + 16 * q, w[0], w[1], w[2], w[3]);
         }
     } else {
-        // byte b holds samples 4b..4b+3 as I0 Q0 I1 Q1 I2 Q2 I3 Q3, MSB first (gpssim.c:2268-2274)
+        // byte b holds samples 4b..4b+3 as I0 Q0 I1 Q1 I2 Q2 I3 Q3, MSB first (gpssim.c:2268-2274);
+        // two bytes (8 samples) per store: a chunk only has to start on a multiple of 8 samples
 #pragma unroll
-        for (int q = 0; q < S / 16; q++) {
+        for (int q = 0; q < S / 8; q++) {
             uint32_t w = 0;
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const int s0 = 16 * q + 4 * b;
+            for (int b = 0; b < 2; b++) {
+                const int s0 = 8 * q + 4 * b;
                 const uint32_t byte = (GS_P01(s0) << 6) | (GS_P01(s0 + 1) << 4) | (GS_P01(s0 + 2) << 2) | GS_P01(s0 + 3);
                 w |= byte << (8 * b);
             }
 #ifdef __CUDA_ARCH__
-            *reinterpret_cast<uint32_t *>(dst + 4 * q) = w;
+            *reinterpret_cast<uint16_t *>(dst + 2 * q) = (uint16_t)w;
 #else
-            memcpy(dst + 4 * q, &w, 4);
+            const uint16_t h = (uint16_t)w;
+            memcpy(dst + 2 * q, &h, 2);
 #endif
         }
     }
@@ -487,8 +511,8 @@ GS_HD void store_run(uint8_t *dst, const typename A::acc_t (&acc)[S])
 // =====================================================================================
 struct GenericChan {
     double x, d;
-    uint32_t ph;
-    int32_t step, gain, icode, bitk;
+    uint32_t phs;      // carr_phase << 7
+    int32_t steps, gain, icode, bitk;
     uint32_t nav_bits;
     const uint32_t *negw;
 };
@@ -502,7 +526,7 @@ GS_HD void generic_sample(GenericChan *ch, int nc, const int16_t *sin512, const 
         const int chip = (int)c.x;
         const int neg = (int)((c.negw[chip >> 5] >> (31 - (chip & 31))) & 1u);
         const int sgn = (neg ? -1 : 1) * data_sign(c.nav_bits, c.bitk);
-        const int it = (int)((c.ph >> 16) & 0x1ffu);
+        const int it = (int)(c.phs >> 23); // (carr_phase >> 16) & 0x1ff, gpssim.c:2202
         i_acc += sgn * (int)cos512[it] * c.gain;
         q_acc += sgn * (int)sin512[it] * c.gain;
         c.x = dadd(c.x, c.d);
@@ -513,7 +537,7 @@ GS_HD void generic_sample(GenericChan *ch, int nc, const int16_t *sin512, const 
                 c.bitk++;
             }
         }
-        c.ph += (uint32_t)c.step;
+        c.phs += (uint32_t)c.steps;
     }
     i16 = (int)(short)((i_acc + 64) >> 7);
     q16 = (int)(short)((q_acc + 64) >> 7);

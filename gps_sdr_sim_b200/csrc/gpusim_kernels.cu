@@ -78,18 +78,76 @@ size_t synth_smem_bytes(int max_active, int threads)
     return kSmemLut + kSmemNegw + (size_t)max_active * threads * 16;
 }
 
+// Shared-memory views of one block.
+template <class A>
+struct K2Smem {
+    typename A::tab_t *lut; // replicated carrier table
+    uint32_t *negw;         // inverted C/A chips, [33][35]
+    double *st_x;           // per channel, per thread: code phase
+    uint32_t *st_phs;       //                          carrier phase << 7
+    uint32_t *st_meta;      //                          icode | bitk<<8 | signed gain<<16
+};
+
+// SR consecutive samples of one thread, all channels, packed and stored.
+// Lanes of a warp vote per channel on whether any of them may reach the 1023-chip wrap inside
+// the run; only then the (longer) wrap-aware loop is taken for that channel.
+template <class A, int FMT, int SR>
+__device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const DevRow *rows, const int nc, const int ncw,
+                                          const bool live, const unsigned mask, const int tid,
+                                          const uint32_t lane_off, const int force_wrap, uint8_t *dst)
+{
+    typename A::acc_t acc[SR];
+#pragma unroll
+    for (int j = 0; j < SR; j++)
+        acc[j] = A::init();
+
+    for (int k = 0; k < ncw; k++) {
+        const bool act = live && k < nc;
+        ChanState st;
+        uint4 r0 = make_uint4(0, 0, 0, 0);
+        uint32_t meta = 0;
+        bool wrap = false;
+        if (act) {
+            r0 = *reinterpret_cast<const uint4 *>(rows + k); // d, steps, cthr | prn | gain8
+            st.x = sm.st_x[k * kK2Threads + tid];
+            st.phs = sm.st_phs[k * kK2Threads + tid];
+            meta = sm.st_meta[k * kK2Threads + tid];
+            wrap = (int)st.x >= (int)(r0.w & 0xffffu) || force_wrap;
+        }
+        const bool any_wrap = __any_sync(mask, wrap);
+        if (act) {
+            const double d = __hiloint2double((int)r0.y, (int)r0.x);
+            const uint32_t steps = r0.z;
+            const uint32_t *nw = sm.negw + ((r0.w >> 16) & 0xffu) * kCaWords;
+            if (!any_wrap) {
+                synth_fast<A, SR>(acc, st, d, steps, meta_sgain(meta), nw, sm.lut, lane_off);
+            } else {
+                const DevRow &r = rows[k];
+                st.icode = meta_icode(meta);
+                st.bitk = meta_bitk(meta);
+                synth_wrap<A, SR>(acc, st, d, steps, r.gain, r.nav_bits, nw, sm.lut, lane_off);
+                sm.st_meta[k * kK2Threads + tid] = pack_meta(st.icode, st.bitk, data_sign(r.nav_bits, st.bitk) * r.gain);
+            }
+            sm.st_x[k * kK2Threads + tid] = st.x;
+            sm.st_phs[k * kK2Threads + tid] = st.phs;
+        }
+    }
+    if (live)
+        store_run<A, FMT, SR>(dst, acc);
+}
+
 template <class A, int FMT, int S>
 __global__ void __launch_bounds__(kK2Threads, 1) k2_synth(DeviceJob job)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     typedef typename A::tab_t tab_t;
-    typedef typename A::acc_t acc_t;
-    tab_t *lut = reinterpret_cast<tab_t *>(smem);
-    uint32_t *negw = reinterpret_cast<uint32_t *>(smem + kSmemLut);
-    uint32_t *lane_tab = negw + kCaPrns * kCaWords;
-    double *st_x = reinterpret_cast<double *>(smem + kSmemLut + kSmemNegw);
-    uint32_t *st_phs = reinterpret_cast<uint32_t *>(st_x + (size_t)job.max_active * kK2Threads);
-    uint32_t *st_meta = st_phs + (size_t)job.max_active * kK2Threads;
+    K2Smem<A> sm;
+    sm.lut = reinterpret_cast<tab_t *>(smem);
+    sm.negw = reinterpret_cast<uint32_t *>(smem + kSmemLut);
+    uint32_t *lane_tab = sm.negw + kCaPrns * kCaWords;
+    sm.st_x = reinterpret_cast<double *>(smem + kSmemLut + kSmemNegw);
+    sm.st_phs = reinterpret_cast<uint32_t *>(sm.st_x + (size_t)job.max_active * kK2Threads);
+    sm.st_meta = sm.st_phs + (size_t)job.max_active * kK2Threads;
 
     const int tid = threadIdx.x;
     // replicated carrier table: entry i, replica r at byte i*128 + r*sizeof(tab_t); a lane always
@@ -99,10 +157,10 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_synth(DeviceJob job)
                                               : reinterpret_cast<const tab_t *>(job.lut_f32);
         constexpr int kPerEntry = 128 / (int)sizeof(tab_t);
         for (int i = tid; i < kLutEntries * kPerEntry; i += kK2Threads)
-            lut[i] = src[i / kPerEntry];
+            sm.lut[i] = src[i / kPerEntry];
     }
     for (int i = tid; i < kCaPrns * kCaWords; i += kK2Threads)
-        negw[i] = job.negw[i];
+        sm.negw[i] = job.negw[i];
     if (tid < 32)
         lane_tab[tid] = (uint32_t)(tid & A::kLaneMask) << A::kLaneShift;
     __syncthreads();
@@ -110,27 +168,42 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_synth(DeviceJob job)
     // this lane's replica offset, read back from shared memory so that ptxas cannot see its
     // value range and keeps (x & 0xff80) | lane_off as ONE LOP3
     const uint32_t lane_off = *reinterpret_cast<volatile uint32_t *>(lane_tab + (tid & 31));
-
-    // Persistent warps: every warp repeatedly claims a unit of 32 consecutive chunks (one per lane).
-    // No block-level synchronisation after the tables are built, so a warp that runs the longer
-    // wrap-checking loop never holds up the others, and the tail of the grid is one unit long.
-    const long long total = (long long)job.n_epochs * job.kc;
     const int lane = tid & 31;
-    const int bytes_per_16 = (FMT == 16) ? 64 : (FMT == 8) ? 32 : 4;
+    constexpr int kBytesPer8 = (FMT == 16) ? 32 : (FMT == 8) ? 16 : 2;
 
+    // Persistent warps: every warp repeatedly claims a unit of 32 chunks, one per lane.  No
+    // block-level synchronisation after the tables are built, so a warp in the wrap-aware loop
+    // never holds up the others, and the tail of the grid is one unit long.
+    //
+    // Which 32 chunks form a unit decides how often the wrap-aware loop runs: a run is slow for a
+    // channel as soon as ONE lane is near that channel's 1023-chip wrap.  In the aligned layout
+    // (ppe > 0) the lanes of a unit are the same slot of 32 consecutive code periods (1 ms of
+    // samples apart), so all lanes see every channel at (almost) the same code phase and the wrap
+    // hits them in the same run; otherwise a unit is 32 consecutive chunks.
     for (;;) {
         unsigned int unit = 0;
         if (lane == 0)
             unit = atomicAdd(job.work_counter, 1u);
         unit = __shfl_sync(0xffffffffu, unit, 0);
-        const long long gid = (long long)unit * 32 + lane;
-        if ((long long)unit * 32 >= total)
+        if (unit >= (unsigned int)job.n_units)
             break;
-        const bool valid = gid < total;
+        int e, jc;
+        bool valid;
+        if (job.ppe > 0) {
+            const unsigned int pg = unit / (unsigned int)job.q;
+            const unsigned int slot = unit - pg * (unsigned int)job.q;
+            const long long period = (long long)pg * 32 + lane;
+            valid = period < (long long)job.n_epochs * job.ppe;
+            e = (int)(period / job.ppe);
+            jc = (int)(period - (long long)e * job.ppe) * job.q + (int)slot;
+        } else {
+            const long long gid = (long long)unit * 32 + lane;
+            valid = gid < (long long)job.n_epochs * job.kc;
+            e = (int)(gid / job.kc);
+            jc = (int)(gid - (long long)e * job.kc);
+        }
         const unsigned mask = __ballot_sync(0xffffffffu, valid);
         if (valid) {
-            const int e = (int)(gid / job.kc);
-            const int jc = (int)(gid - (long long)e * job.kc);
             const int n0 = jc * job.chunk;
             const int nrun = min(job.chunk, job.n_samples - n0);
             const DevRow *rows = job.rows + (size_t)e * kMaxChan;
@@ -141,57 +214,28 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_synth(DeviceJob job)
                 const size_t ck = ((size_t)e * kMaxChan + k) * job.kc + jc;
                 const DevRow r = rows[k];
                 const int ic = (int)r.icode0 + (int)job.ck_w[ck];
-                st_x[k * kK2Threads + tid] = job.ck_x[ck];
-                st_phs[k * kK2Threads + tid] = (r.ph0 + (uint32_t)n0 * (uint32_t)r.step) << 7;
-                st_meta[k * kK2Threads + tid] = (uint32_t)(ic % 20) | ((uint32_t)(ic / 20) << 8);
+                const int bitk = ic / 20;
+                sm.st_x[k * kK2Threads + tid] = job.ck_x[ck];
+                sm.st_phs[k * kK2Threads + tid] = r.ph0s + (uint32_t)n0 * (uint32_t)r.steps;
+                sm.st_meta[k * kK2Threads + tid] = pack_meta(ic - bitk * 20, bitk, data_sign(r.nav_bits, bitk) * r.gain);
             }
 
-            // warp-wide channel and sample counts: every participating lane runs the same number of
-            // loop iterations and takes part in every vote (the last chunk of an epoch is shorter,
+            // warp-wide channel and run counts: every participating lane runs the same number of loop
+            // iterations and takes part in every vote (the last chunk of an epoch may be shorter,
             // epochs may have different numbers of satellites)
             const int ncw = (int)__reduce_max_sync(mask, (unsigned)nc);
-            const int nrun_w = (int)__reduce_max_sync(mask, (unsigned)nrun);
-            uint8_t *outp = job.out + (size_t)e * job.epoch_bytes + (size_t)(n0 / 16) * bytes_per_16;
+            const int full = nrun / S;
+            const int tail8 = (nrun - full * S) / 8;
+            const int full_w = (int)__reduce_max_sync(mask, (unsigned)full);
+            const int tail_w = (int)__reduce_max_sync(mask, (unsigned)tail8);
+            uint8_t *outp = job.out + (size_t)e * job.epoch_bytes + (size_t)(n0 / 8) * kBytesPer8;
 
-            for (int s0 = 0; s0 < nrun_w; s0 += S) {
-                const bool run_live = s0 < nrun;
-                acc_t acc[S];
-#pragma unroll
-                for (int j = 0; j < S; j++)
-                    acc[j] = A::init();
-
-                for (int k = 0; k < ncw; k++) {
-                    const bool act = run_live && k < nc;
-                    ChanState st;
-                    DevRow r;
-                    bool wrap = false;
-                    if (act) {
-                        r = rows[k];
-                        st.x = st_x[k * kK2Threads + tid];
-                        st.phs = st_phs[k * kK2Threads + tid];
-                        const uint32_t meta = st_meta[k * kK2Threads + tid];
-                        st.icode = (int)(meta & 0xffu);
-                        st.bitk = (int)(meta >> 8);
-                        // conservative: a whole extra step of margin over the S rounded adds
-                        wrap = !(st.x + (double)(S + 1) * r.d < (double)kCaLen) || job.force_wrap_path;
-                    }
-                    const bool any_wrap = __any_sync(mask, wrap);
-                    if (act) {
-                        const uint32_t *nw = negw + (size_t)r.prn * kCaWords;
-                        const uint32_t steps = (uint32_t)r.step << 7;
-                        if (!any_wrap) {
-                            synth_fast<A, S>(acc, st, r.d, steps, data_sign(r.nav_bits, st.bitk) * r.gain, nw, lut, lane_off);
-                        } else {
-                            synth_wrap<A, S>(acc, st, r.d, steps, r.gain, r.nav_bits, nw, lut, lane_off);
-                            st_meta[k * kK2Threads + tid] = (uint32_t)st.icode | ((uint32_t)st.bitk << 8);
-                        }
-                        st_x[k * kK2Threads + tid] = st.x;
-                        st_phs[k * kK2Threads + tid] = st.phs;
-                    }
-                }
-                if (run_live)
-                    store_run<A, FMT, S>(outp + (size_t)(s0 / 16) * bytes_per_16, acc);
-            }
+            for (int i = 0; i < full_w; i++)
+                synth_run<A, FMT, S>(sm, rows, nc, ncw, i < full, mask, tid, lane_off, job.force_wrap_path,
+                                     outp + (size_t)i * (S / 8) * kBytesPer8);
+            for (int i = 0; i < tail_w; i++)
+                synth_run<A, FMT, 8>(sm, rows, nc, ncw, i < tail8, mask, tid, lane_off, job.force_wrap_path,
+                                     outp + ((size_t)full * (S / 8) + i) * kBytesPer8);
         }
         __syncwarp();
     }
@@ -221,8 +265,8 @@ __global__ void __launch_bounds__(128) k2_generic(DeviceJob job)
         const int ic = (int)r.icode0 + (int)job.ck_w[ck];
         ch[k].x = job.ck_x[ck];
         ch[k].d = r.d;
-        ch[k].ph = r.ph0 + (uint32_t)n0 * (uint32_t)r.step;
-        ch[k].step = r.step;
+        ch[k].phs = r.ph0s + (uint32_t)n0 * (uint32_t)r.steps;
+        ch[k].steps = r.steps;
         ch[k].gain = r.gain;
         ch[k].icode = ic % 20;
         ch[k].bitk = ic / 20;
@@ -259,7 +303,7 @@ static cudaError_t launch_tuned_a(const DeviceJob &job, cudaStream_t stream)
     cudaError_t err = cudaFuncSetAttribute(k2_synth<A, FMT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess)
         return err;
-    const long long units = ((long long)job.n_epochs * job.kc + 31) / 32;
+    const long long units = job.n_units;
     const long long warps_per_block = kK2Threads / 32;
     const int blocks = (int)std::min<long long>(std::max(1, job.sm_count), (units + warps_per_block - 1) / warps_per_block);
     k2_synth<A, FMT, S><<<blocks, kK2Threads, smem, stream>>>(job);

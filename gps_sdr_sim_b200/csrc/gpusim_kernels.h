@@ -26,7 +26,7 @@ struct DeviceJob {
     unsigned int *work_counter; // zeroed by K1, handed out by K2's warps (32 chunks per unit)
     int32_t n_epochs;
     int32_t n_samples;       // samples per epoch
-    int32_t chunk;           // samples per thread chunk (multiple of 32)
+    int32_t chunk;           // samples per thread chunk (multiple of 8; of 32 when ppe == 0)
     int32_t kc;              // chunks per epoch = ceil(n_samples/chunk)
     int32_t fmt;             // 1 / 8 / 16
     int32_t epoch_bytes;
@@ -34,6 +34,9 @@ struct DeviceJob {
     int32_t force_wrap_path; // test hook: always run the wrap-checking loop
     int32_t accum;           // 0 = AccWide (64-bit IMAD), 1 = AccF32x2 (FFMA2)
     int32_t sm_count;        // persistent K2 grid: one 512-thread block per SM
+    int32_t ppe;             // aligned layout: code periods per epoch (100), chunk = period / q; 0 = plain
+    int32_t q;               // aligned layout: chunks per code period
+    int32_t n_units;         // work units (32 chunks each) of the tuned kernel
 };
 
 enum class ChainAlgo { Jump = 0, Replay = 1 };

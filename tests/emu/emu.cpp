@@ -44,6 +44,31 @@ template <class A> const typename A::tab_t *table_of(const Tables &T);
 template <> const int32_t *table_of<AccWide>(const Tables &T) { return T.lut.data(); }
 template <> const uint64_t *table_of<AccF32x2>(const Tables &T) { return T.lut2.data(); }
 
+// one run of SR samples, all channels (mirrors synth_run in gpusim_kernels.cu, one lane at a time)
+template <class A, int FMT, int SR>
+void emu_run(const Tables &T, const DevRow *rows, int nc, ChanState *st, uint32_t *meta, int force_wrap,
+             uint32_t lane_off, uint8_t *dst)
+{
+    const typename A::tab_t *lut = table_of<A>(T);
+    typename A::acc_t acc[SR];
+    for (int j = 0; j < SR; j++)
+        acc[j] = A::init();
+    for (int k = 0; k < nc; k++) {
+        const DevRow &r = rows[k];
+        const bool wrap = (int)st[k].x >= (int)r.cthr || force_wrap;
+        const uint32_t *nw = T.negw.data() + (size_t)r.prn * kCaWords;
+        if (!wrap) {
+            synth_fast<A, SR>(acc, st[k], r.d, (uint32_t)r.steps, meta_sgain(meta[k]), nw, lut, lane_off);
+        } else {
+            st[k].icode = meta_icode(meta[k]);
+            st[k].bitk = meta_bitk(meta[k]);
+            synth_wrap<A, SR>(acc, st[k], r.d, (uint32_t)r.steps, r.gain, r.nav_bits, nw, lut, lane_off);
+            meta[k] = pack_meta(st[k].icode, st[k].bitk, data_sign(r.nav_bits, st[k].bitk) * r.gain);
+        }
+    }
+    store_run<A, FMT, SR>(dst, acc);
+}
+
 template <class A, int FMT, int S>
 void tuned_chunk(const Tables &T, const DevRow *rows, int nc, const double *ckx, const uint16_t *ckw, int kc,
                  int jc, int chunk, int N, int force_wrap, int lane, uint8_t *epoch_out)
@@ -51,34 +76,22 @@ void tuned_chunk(const Tables &T, const DevRow *rows, int nc, const double *ckx,
     const int n0 = jc * chunk;
     const int nrun = std::min(chunk, N - n0);
     ChanState st[kMaxChan];
+    uint32_t meta[kMaxChan];
     for (int k = 0; k < nc; k++) {
         const int ic = rows[k].icode0 + ckw[k * kc + jc];
+        const int bitk = ic / 20;
         st[k].x = ckx[k * kc + jc];
-        st[k].phs = (rows[k].ph0 + (uint32_t)n0 * (uint32_t)rows[k].step) << 7;
-        st[k].icode = ic % 20;
-        st[k].bitk = ic / 20;
+        st[k].phs = rows[k].ph0s + (uint32_t)n0 * (uint32_t)rows[k].steps;
+        meta[k] = pack_meta(ic - bitk * 20, bitk, data_sign(rows[k].nav_bits, bitk) * rows[k].gain);
     }
-    const int bytes_per_16 = (FMT == 16) ? 64 : (FMT == 8) ? 32 : 4;
-    uint8_t *outp = epoch_out + (size_t)(n0 / 16) * bytes_per_16;
-    const typename A::tab_t *lut = table_of<A>(T);
+    constexpr int kBytesPer8 = (FMT == 16) ? 32 : (FMT == 8) ? 16 : 2;
+    uint8_t *outp = epoch_out + (size_t)(n0 / 8) * kBytesPer8;
     const uint32_t lane_off = (uint32_t)(lane & A::kLaneMask) << A::kLaneShift;
-    for (int s0 = 0; s0 < nrun; s0 += S) {
-        typename A::acc_t acc[S];
-        for (int j = 0; j < S; j++)
-            acc[j] = A::init();
-        for (int k = 0; k < nc; k++) {
-            const DevRow &r = rows[k];
-            const bool wrap = !(st[k].x + (double)(S + 1) * r.d < (double)kCaLen) || force_wrap;
-            const uint32_t *nw = T.negw.data() + (size_t)r.prn * kCaWords;
-            const uint32_t steps = (uint32_t)r.step << 7;
-            if (!wrap) {
-                synth_fast<A, S>(acc, st[k], r.d, steps, data_sign(r.nav_bits, st[k].bitk) * r.gain, nw, lut, lane_off);
-            } else {
-                synth_wrap<A, S>(acc, st[k], r.d, steps, r.gain, r.nav_bits, nw, lut, lane_off);
-            }
-        }
-        store_run<A, FMT, S>(outp + (size_t)(s0 / 16) * bytes_per_16, acc);
-    }
+    const int full = nrun / S, tail8 = (nrun - full * S) / 8;
+    for (int i = 0; i < full; i++)
+        emu_run<A, FMT, S>(T, rows, nc, st, meta, force_wrap, lane_off, outp + (size_t)i * (S / 8) * kBytesPer8);
+    for (int i = 0; i < tail8; i++)
+        emu_run<A, FMT, 8>(T, rows, nc, st, meta, force_wrap, lane_off, outp + ((size_t)full * (S / 8) + i) * kBytesPer8);
 }
 
 template <int FMT>
@@ -93,8 +106,8 @@ void generic_chunk(const Tables &T, const DevRow *rows, int nc, const double *ck
         const int ic = r.icode0 + ckw[k * kc + jc];
         ch[k].x = ckx[k * kc + jc];
         ch[k].d = r.d;
-        ch[k].ph = r.ph0 + (uint32_t)n0 * (uint32_t)r.step;
-        ch[k].step = r.step;
+        ch[k].phs = r.ph0s + (uint32_t)n0 * (uint32_t)r.steps;
+        ch[k].steps = r.steps;
         ch[k].gain = r.gain;
         ch[k].icode = ic % 20;
         ch[k].bitk = ic / 20;
@@ -135,7 +148,8 @@ int emu_generate(const gpusim_epoch_table *t, int N, double delt, int fmt, int c
     static const Tables T;
     const size_t eb = fmt == 1 ? (size_t)(N / 4) : fmt == 8 ? (size_t)2 * N : (size_t)4 * N;
     const int kc = (N + chunk - 1) / chunk;
-    if (chunk % 32 != 0 || (kernel != 2 && N % 32 != 0))
+    // tuned kernels: chunks of a multiple of 8 samples (aligned layout) inside epochs of a multiple of 32
+    if ((kernel == 2 ? chunk % 32 != 0 : chunk % 8 != 0) || (kernel != 2 && N % 32 != 0))
         return -1;
     std::vector<double> ckx((size_t)kMaxChan * kc);
     std::vector<uint16_t> ckw((size_t)kMaxChan * kc);
@@ -149,11 +163,13 @@ int emu_generate(const gpusim_epoch_table *t, int N, double delt, int fmt, int c
                 continue;
             DevRow &o = rows[nc];
             o.d = dmul(t->f_code[r], delt);
-            o.ph0 = t->carr_phase[r];
-            o.step = t->carr_phasestep[r];
+            o.steps = (int32_t)((uint32_t)t->carr_phasestep[r] << 7);
+            o.cthr = wrap_threshold(o.d);
+            o.prn = (uint8_t)t->prn[r];
             o.gain = t->gain[r];
+            o.gain8 = (uint8_t)o.gain;
+            o.ph0s = t->carr_phase[r] << 7;
             o.nav_bits = t->nav_bits[r];
-            o.prn = (uint16_t)t->prn[r];
             o.icode0 = (uint16_t)t->icode[r];
             o.flags = 0;
             if (kernel != 2 && (o.gain < 0 || o.gain > kTunedMaxGain || o.d > (kernel == 0 ? 0.9999 : 2.0)))

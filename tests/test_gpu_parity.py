@@ -41,8 +41,9 @@ def test_cuda_reproduces_reference_bytes(name):
 
 @pytest.mark.parametrize("name", ["static_int_b16", "static_int_b8", "static_int_b1", "nmea_int_1msps_b1",
                                   "satellite_int_b16"])
-@pytest.mark.parametrize("opts", [{"force_slow": 1}, {"force_generic": 1}, {"chain_replay": 1}, {"chunk": 128},
-                                  {"chunk": 2048}, {"chunk": 96}])
+@pytest.mark.parametrize("opts", [{"force_slow": 1}, {"force_generic": 1}, {"chain_replay": 1}, {"accum": 0},
+                                  {"layout": 1}, {"layout": 1, "chunk": 128}, {"layout": 1, "chunk": 2048},
+                                  {"layout": 1, "chunk": 96, "accum": 0}, {"layout": 1, "force_slow": 1}])
 def test_cuda_variants_agree(name, opts):
     table, want, _ = load_golden(name)
     table, want = table.slice(0, 5), want[:5]

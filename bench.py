@@ -124,10 +124,14 @@ def main_reference(args):
 # clocks during the timed region
 # ---------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons every few ms from before the warm-up until after the
+    timed region; `window(t0, t1)` then reports what was seen DURING the timed region."""
+
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.index, self.samples, self.max_mhz, self.error = index, [], None, None
         self._halt = threading.Event()
+        self.ready = threading.Event()
 
     def run(self):
         try:
@@ -139,22 +143,29 @@ class ClockSampler(threading.Thread):
                      pynvml.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
                      pynvml.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown",
                      pynvml.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"}
+            self.ready.set()
             while not self._halt.is_set():
-                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
                 r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
-                time.sleep(0.02)
+                self.samples.append((time.perf_counter(), mhz, tuple(n for b, n in names.items() if r & b)))
+                time.sleep(0.004)
         except Exception as exc:  # noqa: BLE001 - clocks are evidence, not a dependency
-            self.reasons.add(f"sampler_error:{type(exc).__name__}")
+            self.error = f"{type(exc).__name__}: {exc}"
+            self.ready.set()
 
     def stop(self):
         self._halt.set()
         self.join(timeout=2)
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(s)}
+
+    def window(self, t0: float, t1: float):
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        mhz = sorted(s[1] for s in inside)
+        reasons = sorted({r for s in inside for r in s[2]})
+        out = {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+               "samples": len(inside)}
+        if self.error:
+            out["sampler_error"] = self.error
+        return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -217,19 +228,22 @@ def main_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sampler.ready.wait(timeout=20)
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k2_ms, k1_ms = [], []
+    w0 = time.perf_counter()
     ev0.record(stream)
     for _ in range(args.steps):
         step()
     ev1.record(stream)
     barrier()
-    clocks = sampler.stop()
+    w1 = time.perf_counter()
+    clocks = sampler.window(w0, w1)
     ms = ev0.elapsed_time(ev1)
     # per-kernel durations of the last step (CUDA events recorded by the library on the same stream)
     t = sim.timing()
@@ -251,6 +265,7 @@ def main_b200(args):
     torch.cuda.synchronize()
     e2e_sec = time.perf_counter() - t0
     checksum = int(host_out[:: max(1, out_bytes // 65536)].to(torch.int64).sum())   # result is really on the host
+    sampler.stop()
 
     if world > 1:
         tm = torch.tensor([ms, e2e_sec * 1000.0], dtype=torch.float64, device="cuda")
@@ -302,7 +317,7 @@ def main_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()

@@ -236,72 +236,57 @@ struct AccF32x2 {
 //
 // emit(j, x, wraps) is called for sample indices j*every, j = 0 .. ceil(n_total/every)-1.
 // =====================================================================================
-// floor(room / q) for room < 2^53, 2^32 <= q: a float estimate plus one exact correction
-// (a 64-bit division costs several hundred dependent cycles, and this chain is latency bound)
-GS_HD uint64_t div_small_quotient(uint64_t room, uint64_t q)
+GS_HD double dfma(double a, double b, double c) // one rounding of the exact a*b+c
 {
-    const float est = (float)room / (float)q;
-    if (!(est < 1048576.0f))
-        return room / q; // never on real tables: more than 2^20 steps inside one binade
-    uint64_t k = (uint64_t)est;
-    const uint64_t prod = k * q;
-    if (prod > room)
-        k--;
-    else if (room - prod >= q)
-        k++;
-    return k;
+#ifdef __CUDA_ARCH__
+    return __fma_rn(a, b, c);
+#else
+    return __builtin_fma(a, b, c);
+#endif
 }
 
-template <class Emit>
-GS_HD void code_chain(double x, const double d, const int n_total, const int every, Emit emit)
+// The walk is done entirely in FP64: the GPU has no 64-bit integer ALU, but every quantity here
+// (x, the per-binade increment, k increments) is a multiple of ulp(x) below 2^53 ulps, i.e. an
+// exactly representable double, so DADD/DFMA return exact results and one instruction does the
+// work of a multi-instruction 64-bit integer sequence:
+//   delta = (2^e + d) - 2^e   is d rounded to a multiple of ulp(x) exactly as "x + d" rounds it
+//                             (ties go to the even significand, and 2^e has an even one);
+//   x + k*delta               is ONE fma, exact because the result is representable.
+// true if `pred` holds for any thread of `mask` (all of which must call it together); on the host
+// a "warp" is one thread.  Voting also re-converges the threads of the warp.
+GS_HD bool warp_any(unsigned mask, bool pred)
 {
-    const uint64_t db = dbits(d);
-    const int ed = (int)((db >> 52) & 0x7ff) - 1023;
-    const uint64_t dm = (db & 0xfffffffffffffull) | (1ull << 52);
+#ifdef __CUDA_ARCH__
+    return __any_sync(mask, pred);
+#else
+    (void)mask;
+    return pred;
+#endif
+}
+
+// `mask`: the threads of the warp that walk a chain together (device only).
+template <class Emit>
+GS_HD void code_chain(double x, const double d, const int n_total, const int every, Emit emit,
+                      const unsigned mask = 0xffffffffu)
+{
+    const int ed = (int)((dbits(d) >> 52) & 0x7ff) - 1023;
+    const double rd = 1.0 / d; // k = room/delta is estimated with 1/d and then corrected exactly
+    // bit s set: in a binade with ulp = 2^s * ulp(d), d is exactly half an ulp off a multiple
+    uint32_t tie_shifts = 0;
+    {
+        const uint64_t dm = dbits(d) & 0xfffffffffffffull;
+        for (int sft = 1; sft <= 30; sft++)
+            if ((dm & ((1ull << sft) - 1)) == (1ull << (sft - 1)))
+                tie_shifts |= 1u << sft;
+    }
     const int last = ((n_total - 1) / every) * every; // sample index of the last checkpoint
     int n = 0, next = every, j = 1, wraps = 0;
 
-    emit(0, x, 0);
-    while (n < last) {
-        const uint64_t xb = dbits(x);
-        const int ex = (int)((xb >> 52) & 0x7ff) - 1023;
-        const int shift = ex - ed;
-        if (shift >= 1 && shift <= 52) {
-            uint64_t m = (xb & 0xfffffffffffffull) | (1ull << 52);
-            const uint64_t q0 = dm >> shift;
-            const uint64_t rem = dm & ((1ull << shift) - 1);
-            const uint64_t half = 1ull << (shift - 1);
-            uint64_t q = q0 + (rem > half ? 1u : 0u);
-            bool ok = true;
-            if (rem == half) {      // exact tie: round-half-even depends on the parity of m
-                if (m & 1)
-                    ok = false;     // one real step makes m even
-                else
-                    q = q0 + (q0 & 1);
-            }
-            if (ok) {
-                // stay strictly inside the binade and strictly below the 1023 wrap
-                const uint64_t lim = (ex == 9) ? ((uint64_t)kCaLen << 43) : (1ull << 53);
-                uint64_t k = div_small_quotient(lim - 1 - m, q);
-                if (k > (uint64_t)(last - n))
-                    k = (uint64_t)(last - n);
-                const uint64_t ebits = (uint64_t)(ex + 1023) << 52;
-                // checkpoints that fall inside the jump
-                while ((uint64_t)(next - n) <= k) {
-                    const uint64_t mc = m + (uint64_t)(next - n) * q;
-                    emit(j++, dfrombits(ebits | (mc & 0xfffffffffffffull)), wraps);
-                    next += every;
-                }
-                m += k * q;
-                n += (int)k;
-                x = dfrombits(ebits | (m & 0xfffffffffffffull));
-                if (n >= last)
-                    break;
-            }
-        }
-        // one genuine step of gpssim.c:2212-2218
+    // one genuine step of gpssim.c:2212-2218; returns true when it wrapped
+    auto real_step = [&]() -> bool {
         x = dadd(x, d);
-        if (x >= (double)kCaLen) {
+        const bool wrapped = x >= (double)kCaLen;
+        if (wrapped) {
             x = dadd(x, -(double)kCaLen);
             wraps++;
         }
@@ -309,6 +294,66 @@ GS_HD void code_chain(double x, const double d, const int n_total, const int eve
         if (n == next) {
             emit(j++, x, wraps);
             next += every;
+        }
+        return wrapped;
+    };
+    auto shift_of = [&](double v) -> int { return (int)((dbits(v) >> 52) & 0x7ff) - 1023 - ed; };
+
+    // The loops are shaped so that the threads of a warp - the same satellite in 32 consecutive
+    // epochs, i.e. chains that cross the binades and the wrap at nearly the same sample - take the
+    // same number of trips and re-converge once per code period: one trip of the outer loop is one
+    // code period, one trip of loop B is one binade (a jump and the real step across its edge).
+    // The vote at the top of every period keeps the warp together (threads that are done idle).
+    emit(0, x, 0);
+    while (warp_any(mask, n < last)) {
+        // A: the low binades hold only a handful of samples (2^shift/1.x each): real additions
+        while (n < last && shift_of(x) < 4)
+            real_step();
+        // B: one binade per trip, until the chain wraps (shift <= 30 keeps k inside an int); the
+        // vote per trip keeps the warp on the same binade
+        bool in_period = n < last;
+        while (warp_any(mask, in_period)) {
+            if (!in_period)
+                continue;
+            const uint64_t xb = dbits(x);
+            const int bex = (int)((xb >> 52) & 0x7ff); // biased exponent of x
+            const int shift = bex - 1023 - ed;
+            // exact tie (d is half an ulp of x away from a multiple of that ulp): from an odd
+            // significand the rounding goes the other way once - take the real step, after it the
+            // significand is even for good
+            const bool tie_odd = ((tie_shifts >> (shift & 31)) & (uint32_t)xb & 1u) != 0;
+            if (shift >= 4 && shift <= 30 && !tie_odd) {
+                const double c = dfrombits((uint64_t)bex << 52);        // 2^e
+                const double u = dfrombits((uint64_t)(bex - 52) << 52); // ulp(x)
+                const double lim = (bex == 1023 + 9) ? (double)kCaLen : dadd(c, c);
+                const double delta = dadd(dadd(c, d), -c);
+                const double top = dadd(lim, -u);  // stay strictly inside the binade / below the wrap
+                const double room = dadd(top, -x); // exact, >= 0
+                int k = (int)(room * rd);
+                double y = dfma((double)k, delta, x);
+                if (y > top) {
+                    k--;
+                    y = dfma((double)k, delta, x);
+                } else if (dadd(top, -y) >= delta) {
+                    k++;
+                    y = dfma((double)k, delta, x);
+                }
+                if (k > last - n) {
+                    k = last - n;
+                    y = dfma((double)k, delta, x);
+                }
+                if (k > 0 && y <= top) {
+                    // checkpoints that fall inside the jump
+                    while (next - n <= k) {
+                        emit(j++, dfma((double)(next - n), delta, x), wraps);
+                        next += every;
+                    }
+                    x = y;
+                    n += k;
+                }
+            }
+            if (n >= last || real_step())
+                in_period = false;
         }
     }
 }

@@ -22,14 +22,19 @@ namespace gpusim {
 // K1
 // ------------------------------------------------------------------------------------
 template <bool kReplay>
-__global__ void __launch_bounds__(128) k1_chain(DeviceJob job)
+__global__ void __launch_bounds__(32) k1_chain(DeviceJob job)
 {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx == 0)
+    // One warp = ONE channel slot over 32 consecutive epochs.  The host re-derives the code phase
+    // from the pseudorange every epoch, but the signal is continuous, so the same satellite starts
+    // consecutive epochs at almost the same code phase: the 32 chains of a warp cross binades and
+    // wrap nearly in lockstep and the walk (a serial, latency-bound loop) hardly diverges.
+    if (blockIdx.x == 0 && threadIdx.x == 0)
         *job.work_counter = 0; // K2 of the same job runs after this kernel on the same stream
-    const int e = idx / kMaxChan;
-    const int k = idx % kMaxChan;
-    if (e >= job.n_epochs || k >= job.nch[e])
+    const int k = blockIdx.x % kMaxChan;
+    const int e = (blockIdx.x / kMaxChan) * 32 + threadIdx.x;
+    const bool has_chain = e < job.n_epochs && k < job.nch[min(e, job.n_epochs - 1)];
+    const unsigned mask = __ballot_sync(0xffffffffu, has_chain);
+    if (!has_chain)
         return;
     const size_t row = (size_t)e * kMaxChan + k;
     const double d = job.rows[row].d;
@@ -43,14 +48,14 @@ __global__ void __launch_bounds__(128) k1_chain(DeviceJob job)
     if (kReplay)
         code_chain_replay(x0, d, job.n_samples, job.chunk, emit);
     else
-        code_chain(x0, d, job.n_samples, job.chunk, emit);
+        code_chain(x0, d, job.n_samples, job.chunk, emit, mask);
 }
 
 cudaError_t launch_chain(const DeviceJob &job, ChainAlgo algo, cudaStream_t stream)
 {
-    const int threads = 128;
-    const int total = job.n_epochs * kMaxChan;
-    const int blocks = (total + threads - 1) / threads;
+    // Latency-bound serial chains, few of them: one warp per block spreads them over all SMs.
+    const int threads = 32;
+    const int blocks = ((job.n_epochs + 31) / 32) * kMaxChan;
     if (blocks == 0)
         return cudaSuccess;
     if (algo == ChainAlgo::Replay)
@@ -63,7 +68,10 @@ cudaError_t launch_chain(const DeviceJob &job, ChainAlgo algo, cudaStream_t stre
 // ------------------------------------------------------------------------------------
 // K2 tuned
 // ------------------------------------------------------------------------------------
-constexpr int kK2Threads = 512;
+#ifndef GS_K2_THREADS
+#define GS_K2_THREADS 512
+#endif
+constexpr int kK2Threads = GS_K2_THREADS;
 
 int synth_threads() { return kK2Threads; }
 
@@ -78,41 +86,67 @@ size_t synth_smem_bytes(int max_active, int threads)
     return kSmemLut + kSmemNegw + (size_t)max_active * threads * 16;
 }
 
-// Shared-memory views of one block.
+// Shared-memory views of one block.  Per-thread channel state lives in shared memory (it does not
+// fit in registers next to 32 accumulators): channel k, thread t at byte k*16*T + t*8 holds the code
+// phase (f64) and 8*T bytes further the pair (carrier phase << 7, icode | bitk<<8 | signed gain<<16).
+// It is addressed with 32-bit shared-window addresses so that the per-channel address update is a
+// single integer add.
 template <class A>
 struct K2Smem {
     typename A::tab_t *lut; // replicated carrier table
     uint32_t *negw;         // inverted C/A chips, [33][35]
-    double *st_x;           // per channel, per thread: code phase
-    uint32_t *st_phs;       //                          carrier phase << 7
-    uint32_t *st_meta;      //                          icode | bitk<<8 | signed gain<<16
+    uint32_t state;         // shared-window address of this thread's slot for channel 0
 };
+constexpr uint32_t kStateStride = 16u * kK2Threads; // bytes between channels
+constexpr uint32_t kStatePm = 8u * kK2Threads;      // offset of the (phs, meta) pair
+
+__device__ __forceinline__ double lds_f64(uint32_t a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u32x2(uint32_t a)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v)); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ void sts_u32x2(uint32_t a, uint32_t v0, uint32_t v1)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v0), "r"(v1));
+}
 
 // SR consecutive samples of one thread, all channels, packed and stored.
 // Lanes of a warp vote per channel on whether any of them may reach the 1023-chip wrap inside
 // the run; only then the (longer) wrap-aware loop is taken for that channel.
+// rows4: this epoch's rows as uint4 pairs; cthr_mask: 0xffff, or 0 to force the wrap-aware loop.
 template <class A, int FMT, int SR>
-__device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const DevRow *rows, const int nc, const int ncw,
-                                          const bool live, const unsigned mask, const int tid,
-                                          const uint32_t lane_off, const int force_wrap, uint8_t *dst)
+__device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows4, const int nc, const int ncw,
+                                          const bool live, const unsigned mask, const uint32_t lane_off,
+                                          const uint32_t cthr_mask, uint8_t *dst)
 {
     typename A::acc_t acc[SR];
 #pragma unroll
     for (int j = 0; j < SR; j++)
         acc[j] = A::init();
 
-    for (int k = 0; k < ncw; k++) {
+    uint32_t sa = sm.state;
+    for (int k = 0; k < ncw; k++, sa += kStateStride) {
         const bool act = live && k < nc;
         ChanState st;
         uint4 r0 = make_uint4(0, 0, 0, 0);
         uint32_t meta = 0;
         bool wrap = false;
         if (act) {
-            r0 = *reinterpret_cast<const uint4 *>(rows + k); // d, steps, cthr | prn | gain8
-            st.x = sm.st_x[k * kK2Threads + tid];
-            st.phs = sm.st_phs[k * kK2Threads + tid];
-            meta = sm.st_meta[k * kK2Threads + tid];
-            wrap = (int)st.x >= (int)(r0.w & 0xffffu) || force_wrap;
+            r0 = rows4[2 * k]; // d, steps, cthr | prn<<16 | gain8<<24
+            st.x = lds_f64(sa);
+            const uint2 pm = lds_u32x2(sa + kStatePm);
+            st.phs = pm.x;
+            meta = pm.y;
+            wrap = (int)st.x >= (int)(r0.w & cthr_mask);
         }
         const bool any_wrap = __any_sync(mask, wrap);
         if (act) {
@@ -122,14 +156,14 @@ __device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const DevRow *row
             if (!any_wrap) {
                 synth_fast<A, SR>(acc, st, d, steps, meta_sgain(meta), nw, sm.lut, lane_off);
             } else {
-                const DevRow &r = rows[k];
+                const uint4 r1 = rows4[2 * k + 1]; // ph0s, gain, nav_bits, icode0 | flags<<16
                 st.icode = meta_icode(meta);
                 st.bitk = meta_bitk(meta);
-                synth_wrap<A, SR>(acc, st, d, steps, r.gain, r.nav_bits, nw, sm.lut, lane_off);
-                sm.st_meta[k * kK2Threads + tid] = pack_meta(st.icode, st.bitk, data_sign(r.nav_bits, st.bitk) * r.gain);
+                synth_wrap<A, SR>(acc, st, d, steps, (int32_t)r1.y, r1.z, nw, sm.lut, lane_off);
+                sts_u32(sa + kStatePm + 4, pack_meta(st.icode, st.bitk, data_sign(r1.z, st.bitk) * (int32_t)r1.y));
             }
-            sm.st_x[k * kK2Threads + tid] = st.x;
-            sm.st_phs[k * kK2Threads + tid] = st.phs;
+            sts_f64(sa, st.x);
+            sts_u32(sa + kStatePm, st.phs);
         }
     }
     if (live)
@@ -145,11 +179,9 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_synth(DeviceJob job)
     sm.lut = reinterpret_cast<tab_t *>(smem);
     sm.negw = reinterpret_cast<uint32_t *>(smem + kSmemLut);
     uint32_t *lane_tab = sm.negw + kCaPrns * kCaWords;
-    sm.st_x = reinterpret_cast<double *>(smem + kSmemLut + kSmemNegw);
-    sm.st_phs = reinterpret_cast<uint32_t *>(sm.st_x + (size_t)job.max_active * kK2Threads);
-    sm.st_meta = sm.st_phs + (size_t)job.max_active * kK2Threads;
 
     const int tid = threadIdx.x;
+    sm.state = (uint32_t)__cvta_generic_to_shared(smem + kSmemLut + kSmemNegw) + (uint32_t)tid * 8u;
     // replicated carrier table: entry i, replica r at byte i*128 + r*sizeof(tab_t); a lane always
     // reads its own replica, so no lookup ever has a bank conflict
     {
@@ -169,6 +201,7 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_synth(DeviceJob job)
     // value range and keeps (x & 0xff80) | lane_off as ONE LOP3
     const uint32_t lane_off = *reinterpret_cast<volatile uint32_t *>(lane_tab + (tid & 31));
     const int lane = tid & 31;
+    const uint32_t cthr_mask = job.force_wrap_path ? 0u : 0xffffu;
     constexpr int kBytesPer8 = (FMT == 16) ? 32 : (FMT == 8) ? 16 : 2;
 
     // Persistent warps: every warp repeatedly claims a unit of 32 chunks, one per lane.  No
@@ -207,17 +240,19 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_synth(DeviceJob job)
             const int n0 = jc * job.chunk;
             const int nrun = min(job.chunk, job.n_samples - n0);
             const DevRow *rows = job.rows + (size_t)e * kMaxChan;
+            const uint4 *rows4 = reinterpret_cast<const uint4 *>(rows);
             const int nc = job.nch[e];
 
             // chunk-start state of every channel
-            for (int k = 0; k < nc; k++) {
+            uint32_t sa = sm.state;
+            for (int k = 0; k < nc; k++, sa += kStateStride) {
                 const size_t ck = ((size_t)e * kMaxChan + k) * job.kc + jc;
                 const DevRow r = rows[k];
                 const int ic = (int)r.icode0 + (int)job.ck_w[ck];
                 const int bitk = ic / 20;
-                sm.st_x[k * kK2Threads + tid] = job.ck_x[ck];
-                sm.st_phs[k * kK2Threads + tid] = r.ph0s + (uint32_t)n0 * (uint32_t)r.steps;
-                sm.st_meta[k * kK2Threads + tid] = pack_meta(ic - bitk * 20, bitk, data_sign(r.nav_bits, bitk) * r.gain);
+                sts_f64(sa, job.ck_x[ck]);
+                sts_u32x2(sa + kStatePm, r.ph0s + (uint32_t)n0 * (uint32_t)r.steps,
+                          pack_meta(ic - bitk * 20, bitk, data_sign(r.nav_bits, bitk) * r.gain));
             }
 
             // warp-wide channel and run counts: every participating lane runs the same number of loop
@@ -231,10 +266,10 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_synth(DeviceJob job)
             uint8_t *outp = job.out + (size_t)e * job.epoch_bytes + (size_t)(n0 / 8) * kBytesPer8;
 
             for (int i = 0; i < full_w; i++)
-                synth_run<A, FMT, S>(sm, rows, nc, ncw, i < full, mask, tid, lane_off, job.force_wrap_path,
+                synth_run<A, FMT, S>(sm, rows4, nc, ncw, i < full, mask, lane_off, cthr_mask,
                                      outp + (size_t)i * (S / 8) * kBytesPer8);
             for (int i = 0; i < tail_w; i++)
-                synth_run<A, FMT, 8>(sm, rows, nc, ncw, i < tail8, mask, tid, lane_off, job.force_wrap_path,
+                synth_run<A, FMT, 8>(sm, rows4, nc, ncw, i < tail8, mask, lane_off, cthr_mask,
                                      outp + ((size_t)full * (S / 8) + i) * kBytesPer8);
         }
         __syncwarp();

@@ -31,6 +31,9 @@ __global__ void __launch_bounds__(512, 1) probe(uint64_t *sink, double dseed, in
             if (MODE == 5) { w[i] = w[i] * iseed + it; }                                  // IMAD
             if (MODE == 6) { w[i] = (w[i] << 3) ^ (w[i] >> 5); }                          // SHF/LOP
             if (MODE == 7) { asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+r"(w[i]) : "r"(iseed)); } // FFMA
+            if (MODE == 8) { w[i] = (int32_t)__umulhi((uint32_t)w[i], 0x10001u + it); }           // IMAD.HI
+            if (MODE == 9) { a[i] = __dadd_rd(a[i], d); }                                        // DADD.RM
+            if (MODE == 10) { asm volatile("prmt.b32 %0, %0, %1, 0x5432;" : "+r"(w[i]) : "r"(iseed)); } // PRMT
         }
     }
     uint64_t acc = 0;
@@ -69,5 +72,8 @@ int main()
     run<5>("IMAD", sink, sms);
     run<6>("SHF+SHF+LOP3", sink, sms);
     run<7>("FFMA", sink, sms);
+    run<8>("IMAD.HI.U32", sink, sms);
+    run<9>("DADD.RM", sink, sms);
+    run<10>("PRMT", sink, sms);
     return 0;
 }

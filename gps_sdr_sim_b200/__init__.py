@@ -5,8 +5,9 @@ Only the hot path of the reference (gpssim.c:2190-2288) lives here: the CUDA lib
 """
 from .table import (CARRIER_FLOAT, CARRIER_INT, MAX_CHAN, SC01, SC08, SC16, EpochTable, epoch_bytes,
                     synthetic_table)
-from .api import GpuSim, GpuSimError, Timing, ca_code, carrier_lut, library_path, load_library, pack_nav_bits
+from .api import (GpuSim, GpuSimError, Timing, advance_carrier_f64, ca_code, carrier_lut, library_path, load_library,
+                  pack_nav_bits)
 
 __all__ = ["GpuSim", "GpuSimError", "Timing", "EpochTable", "epoch_bytes", "synthetic_table", "ca_code",
-           "carrier_lut", "pack_nav_bits", "load_library", "library_path", "MAX_CHAN", "SC01", "SC08", "SC16",
+           "carrier_lut", "pack_nav_bits", "advance_carrier_f64", "load_library", "library_path", "MAX_CHAN", "SC01", "SC08", "SC16",
            "CARRIER_INT", "CARRIER_FLOAT"]

@@ -45,7 +45,7 @@ EXPORTS = (
     "gpusim_abi_version", "gpusim_strerror", "gpusim_last_error", "gpusim_create", "gpusim_destroy",
     "gpusim_epoch_bytes", "gpusim_generate_epochs", "gpusim_generate_epochs_to_sink",
     "gpusim_upload_table", "gpusim_generate_device", "gpusim_get_timing", "gpusim_set_option",
-    "gpusim_carrier_lut", "gpusim_ca_code", "gpusim_pack_nav_bits",
+    "gpusim_carrier_lut", "gpusim_ca_code", "gpusim_pack_nav_bits", "gpusim_advance_carrier_f64",
 )
 
 
@@ -93,6 +93,8 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.gpusim_ca_code.argtypes = [i32, vp]
     lib.gpusim_pack_nav_bits.restype = ctypes.c_uint32
     lib.gpusim_pack_nav_bits.argtypes = [vp, i32, i32, i32]
+    lib.gpusim_advance_carrier_f64.restype = ctypes.c_double
+    lib.gpusim_advance_carrier_f64.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_double, i32]
     _lib = lib
     return lib
 
@@ -118,6 +120,11 @@ def ca_code(prn: int) -> np.ndarray:
 def pack_nav_bits(dwrd, iword: int, ibit: int) -> int:
     a = np.ascontiguousarray(np.asarray(dwrd, dtype=np.uint64))
     return int(load_library().gpusim_pack_nav_bits(a.ctypes.data, a.size, iword, ibit))
+
+
+def advance_carrier_f64(carr_phase: float, f_carr: float, delt: float, n_samples: int) -> float:
+    """chan[i].carr_phase after n_samples FLOAT_CARR_PHASE updates (gpssim.c:2245-2250), exactly."""
+    return float(load_library().gpusim_advance_carrier_f64(carr_phase, f_carr, delt, n_samples))
 
 
 class GpuSim:

@@ -54,6 +54,8 @@ struct gpusim_ctx {
     double *d_ck_x = nullptr;
     uint16_t *d_ck_w = nullptr;
     unsigned int *d_work = nullptr;
+    // FLOAT_CARR_PHASE hosts: 512*RN(f_carr*delt), 512*carr_phase at epoch start, carrier checkpoints
+    double *d_dc = nullptr, *h_dc = nullptr, *d_cph0 = nullptr, *h_cph0 = nullptr, *d_ck_c = nullptr;
     int sm_count = 148;
     int min_chunk = 128;
 
@@ -129,6 +131,10 @@ SynthKernel plan_job(gpusim_ctx *ctx, int first, int n, uint8_t *out_dev, Device
     job.x0 = ctx->d_x0 + (size_t)first * kMaxChan;
     job.ck_x = ctx->d_ck_x;
     job.ck_w = ctx->d_ck_w;
+    job.carrier_float = ctx->cfg.carrier_mode == GPUSIM_CARRIER_FLOAT ? 1 : 0;
+    job.dc = ctx->d_dc ? ctx->d_dc + (size_t)first * kMaxChan : nullptr;
+    job.cph0 = ctx->d_cph0 ? ctx->d_cph0 + (size_t)first * kMaxChan : nullptr;
+    job.ck_c = ctx->d_ck_c;
     job.lut_wide = ctx->d_lut;
     job.lut_f32 = ctx->d_lut_f32;
     job.accum = ctx->opt_accum;
@@ -195,6 +201,11 @@ DeviceJob sub_job(const gpusim_ctx *ctx, const DeviceJob &whole, int first, int 
     job.x0 = whole.x0 + (size_t)first * kMaxChan;
     job.ck_x = whole.ck_x + (size_t)first * kMaxChan * whole.kc;
     job.ck_w = whole.ck_w + (size_t)first * kMaxChan * whole.kc;
+    if (whole.carrier_float) {
+        job.dc = whole.dc + (size_t)first * kMaxChan;
+        job.cph0 = whole.cph0 + (size_t)first * kMaxChan;
+        job.ck_c = whole.ck_c + (size_t)first * kMaxChan * whole.kc;
+    }
     job.out = out_dev;
     job.n_epochs = n;
     job.n_units = job.ppe > 0 ? (int32_t)((((long long)n * job.ppe + 31) / 32) * job.q)
@@ -268,6 +279,8 @@ void gpusim_destroy(gpusim_ctx *ctx)
     cudaFree(ctx->d_lut); cudaFree(ctx->d_lut_f32); cudaFree(ctx->d_sin16); cudaFree(ctx->d_cos16); cudaFree(ctx->d_negw);
     cudaFree(ctx->d_rows); cudaFree(ctx->d_nch); cudaFree(ctx->d_x0);
     cudaFree(ctx->d_ck_x); cudaFree(ctx->d_ck_w); cudaFree(ctx->d_work); cudaFree(ctx->d_out);
+    cudaFree(ctx->d_dc); cudaFree(ctx->d_cph0); cudaFree(ctx->d_ck_c);
+    cudaFreeHost(ctx->h_dc); cudaFreeHost(ctx->h_cph0);
     cudaFreeHost(ctx->h_rows); cudaFreeHost(ctx->h_nch); cudaFreeHost(ctx->h_x0);
     cudaFreeHost(ctx->h_stage[0]); cudaFreeHost(ctx->h_stage[1]);
     for (cudaEvent_t ev : {ctx->ev_t0, ctx->ev_t1, ctx->ev_t2, ctx->ev_done[0], ctx->ev_done[1],
@@ -289,10 +302,7 @@ int gpusim_create(const gpusim_config *cfg, gpusim_ctx **out_ctx)
         return fail(nullptr, GPUSIM_ERR_ARG, "samples_per_epoch, max_batch_epochs and delt must be positive");
     if (cfg->data_format != GPUSIM_SC01 && cfg->data_format != GPUSIM_SC08 && cfg->data_format != GPUSIM_SC16)
         return fail(nullptr, GPUSIM_ERR_ARG, "data_format must be 1, 8 or 16");
-    if (cfg->carrier_mode == GPUSIM_CARRIER_FLOAT)
-        return fail(nullptr, GPUSIM_ERR_UNSUPPORTED,
-                    "FLOAT_CARR_PHASE hosts are not supported yet: build the host with gpssim.h:4 disabled");
-    if (cfg->carrier_mode != GPUSIM_CARRIER_INT)
+    if (cfg->carrier_mode != GPUSIM_CARRIER_INT && cfg->carrier_mode != GPUSIM_CARRIER_FLOAT)
         return fail(nullptr, GPUSIM_ERR_ARG, "unknown carrier_mode");
 
     int ndev = 0;
@@ -368,14 +378,23 @@ int gpusim_create(const gpusim_config *cfg, gpusim_ctx **out_ctx)
     GS_CREATE(cudaMallocHost(&ctx->h_nch, (size_t)cfg->max_batch_epochs));
     GS_CREATE(cudaMallocHost(&ctx->h_x0, rows * sizeof(double)));
 
-    // checkpoints: 10 bytes per (row, chunk); raise the minimum chunk until they fit the budget
+    // checkpoints: 10 (18 with a double carrier) bytes per (row, chunk); raise the minimum chunk until
+    // they fit the budget
+    const bool cf = cfg->carrier_mode == GPUSIM_CARRIER_FLOAT;
     ctx->min_chunk = 128;
-    while (rows * (size_t)kc_for(N, ctx->min_chunk) * 10 > kCheckpointBudget && ctx->min_chunk < (1 << 20))
+    while (rows * (size_t)kc_for(N, ctx->min_chunk) * (cf ? 18 : 10) > kCheckpointBudget && ctx->min_chunk < (1 << 20))
         ctx->min_chunk *= 2;
     const size_t cks = rows * (size_t)kc_for(N, ctx->min_chunk);
     GS_CREATE(cudaMalloc(&ctx->d_ck_x, cks * sizeof(double)));
     GS_CREATE(cudaMalloc(&ctx->d_ck_w, cks * sizeof(uint16_t)));
     GS_CREATE(cudaMalloc(&ctx->d_work, 64));
+    if (cf) {
+        GS_CREATE(cudaMalloc(&ctx->d_ck_c, cks * sizeof(double)));
+        GS_CREATE(cudaMalloc(&ctx->d_dc, rows * sizeof(double)));
+        GS_CREATE(cudaMalloc(&ctx->d_cph0, rows * sizeof(double)));
+        GS_CREATE(cudaMallocHost(&ctx->h_dc, rows * sizeof(double)));
+        GS_CREATE(cudaMallocHost(&ctx->h_cph0, rows * sizeof(double)));
+    }
     GS_CREATE(cudaMemset(ctx->d_work, 0, 64));
     GS_CREATE(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
 #undef GS_CREATE
@@ -404,8 +423,13 @@ int gpusim_upload_table(gpusim_ctx *ctx, const gpusim_epoch_table *t)
         return GPUSIM_ERR_ARG;
     if (t->n_epochs < 0 || t->n_epochs > ctx->cfg.max_batch_epochs)
         return fail(ctx, GPUSIM_ERR_CAPACITY, "table has %d epochs, context capacity is %d", t->n_epochs, ctx->cfg.max_batch_epochs);
-    if (!t->prn || !t->f_code || !t->code_phase || !t->icode || !t->nav_bits || !t->gain || !t->carr_phasestep || !t->carr_phase)
-        return fail(ctx, GPUSIM_ERR_ARG, "integer-carrier tables need prn, f_code, code_phase, icode, nav_bits, gain, carr_phasestep, carr_phase");
+    const bool cf = ctx->cfg.carrier_mode == GPUSIM_CARRIER_FLOAT;
+    if (!t->prn || !t->f_code || !t->code_phase || !t->icode || !t->nav_bits || !t->gain)
+        return fail(ctx, GPUSIM_ERR_ARG, "tables need prn, f_code, code_phase, icode, nav_bits, gain");
+    if (!cf && (!t->carr_phasestep || !t->carr_phase))
+        return fail(ctx, GPUSIM_ERR_ARG, "integer-carrier tables need carr_phasestep and carr_phase");
+    if (cf && (!t->f_carr || !t->carr_phase_f))
+        return fail(ctx, GPUSIM_ERR_ARG, "FLOAT_CARR_PHASE tables need f_carr and carr_phase_f");
     GS_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     // the previous upload may still be read by kernels in flight
     GS_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
@@ -427,10 +451,19 @@ int gpusim_upload_table(gpusim_ctx *ctx, const gpusim_epoch_table *t)
                 return fail(ctx, GPUSIM_ERR_ARG, "epoch %d slot %d: code_phase %.17g, f_code*delt %.17g or icode %d outside the reference's invariants", e, i, x0, (double)d, t->icode[r]);
             DevRow &o = ctx->h_rows[(size_t)e * kMaxChan + nc];
             o.d = d;
-            o.steps = (int32_t)((uint32_t)t->carr_phasestep[r] << 7);
+            o.steps = cf ? 0 : (int32_t)((uint32_t)t->carr_phasestep[r] << 7);
             o.cthr = wrap_threshold(d);
             o.prn = (uint8_t)t->prn[r];
-            o.ph0s = t->carr_phase[r] << 7;
+            o.ph0s = cf ? 0u : t->carr_phase[r] << 7;
+            if (cf) {
+                // gpssim.c:2245: carr_phase += f_carr*delt (rounded product), phase in [0,1); kept x512
+                const volatile double dcar = t->f_carr[r] * delt;
+                const double cp = t->carr_phase_f[r];
+                if (!(cp >= 0.0 && cp < 1.0) || !(dcar > -1.0 && dcar < 1.0))
+                    return fail(ctx, GPUSIM_ERR_ARG, "epoch %d slot %d: carr_phase %.17g or f_carr*delt %.17g outside [0,1) / (-1,1)", e, i, cp, (double)dcar);
+                ctx->h_dc[(size_t)e * kMaxChan + nc] = dcar * 512.0;
+                ctx->h_cph0[(size_t)e * kMaxChan + nc] = cp * 512.0;
+            }
             o.gain = t->gain[r];
             o.nav_bits = t->nav_bits[r];
             o.icode0 = (uint16_t)t->icode[r];
@@ -449,6 +482,10 @@ int gpusim_upload_table(gpusim_ctx *ctx, const gpusim_epoch_table *t)
         for (int k = nc; k < kMaxChan; k++) {
             memset(&ctx->h_rows[(size_t)e * kMaxChan + k], 0, sizeof(DevRow));
             ctx->h_x0[(size_t)e * kMaxChan + k] = 0.0;
+            if (cf) {
+                ctx->h_dc[(size_t)e * kMaxChan + k] = 0.0;
+                ctx->h_cph0[(size_t)e * kMaxChan + k] = 0.0;
+            }
         }
         ctx->h_nch[e] = (uint8_t)nc;
     }
@@ -457,6 +494,10 @@ int gpusim_upload_table(gpusim_ctx *ctx, const gpusim_epoch_table *t)
         GS_CUDA(ctx, cudaMemcpyAsync(ctx->d_rows, ctx->h_rows, rows * sizeof(DevRow), cudaMemcpyHostToDevice, ctx->s_compute));
         GS_CUDA(ctx, cudaMemcpyAsync(ctx->d_x0, ctx->h_x0, rows * sizeof(double), cudaMemcpyHostToDevice, ctx->s_compute));
         GS_CUDA(ctx, cudaMemcpyAsync(ctx->d_nch, ctx->h_nch, (size_t)t->n_epochs, cudaMemcpyHostToDevice, ctx->s_compute));
+        if (cf) {
+            GS_CUDA(ctx, cudaMemcpyAsync(ctx->d_dc, ctx->h_dc, rows * sizeof(double), cudaMemcpyHostToDevice, ctx->s_compute));
+            GS_CUDA(ctx, cudaMemcpyAsync(ctx->d_cph0, ctx->h_cph0, rows * sizeof(double), cudaMemcpyHostToDevice, ctx->s_compute));
+        }
         GS_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
     }
     ctx->n_uploaded = t->n_epochs;

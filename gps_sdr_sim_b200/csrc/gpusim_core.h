@@ -264,32 +264,44 @@ GS_HD bool warp_any(unsigned mask, bool pred)
 #endif
 }
 
-// `mask`: the threads of the warp that walk a chain together (device only).
+// Exact walk of the recurrence
+//     x += d;  if (x >= M) x -= M;  else if (x < 0) x += M;          (|d| < M, either sign)
+// for n_end steps; emit(j, x, wraps) at step indices j*every (j >= 0, j*every <= n_end); returns
+// the value after n_end steps.  Two users:
+//   code phase    M = 1023, d = RN(f_code*delt) > 0                    gpssim.c:2212-2218
+//   carrier phase M = 512,  d = 512*RN(f_carr*delt), x = 512*carr_phase (FLOAT_CARR_PHASE hosts;
+//                 the power-of-two scaling commutes with every rounding)   gpssim.c:2245-2250
+// `mask`: the threads of the warp that walk chains together (device only).
 template <class Emit>
-GS_HD void code_chain(double x, const double d, const int n_total, const int every, Emit emit,
-                      const unsigned mask = 0xffffffffu)
+GS_HD double phase_chain(double x, const double d, const double M, const int n_end, const int every,
+                         Emit emit, const unsigned mask = 0xffffffffu)
 {
-    const int ed = (int)((dbits(d) >> 52) & 0x7ff) - 1023;
-    const double rd = 1.0 / d; // k = room/delta is estimated with 1/d and then corrected exactly
+    const bool neg = d < 0.0;
+    const double ad = neg ? -d : d;
+    const int ed = (int)((dbits(ad) >> 52) & 0x7ff) - 1023;
+    const double rd = 1.0 / ad; // k = room/|delta| is estimated with 1/|d| and then corrected exactly
     // bit s set: in a binade with ulp = 2^s * ulp(d), d is exactly half an ulp off a multiple
     uint32_t tie_shifts = 0;
     {
-        const uint64_t dm = dbits(d) & 0xfffffffffffffull;
+        const uint64_t dm = dbits(ad) & 0xfffffffffffffull;
         for (int sft = 1; sft <= 30; sft++)
             if ((dm & ((1ull << sft) - 1)) == (1ull << (sft - 1)))
                 tie_shifts |= 1u << sft;
     }
-    const int last = ((n_total - 1) / every) * every; // sample index of the last checkpoint
     int n = 0, next = every, j = 1, wraps = 0;
 
-    // one genuine step of gpssim.c:2212-2218; returns true when it wrapped
+    // one genuine step; returns true when it wrapped
     auto real_step = [&]() -> bool {
         x = dadd(x, d);
-        const bool wrapped = x >= (double)kCaLen;
-        if (wrapped) {
-            x = dadd(x, -(double)kCaLen);
-            wraps++;
+        bool wrapped = false;
+        if (x >= M) {
+            x = dadd(x, -M);
+            wrapped = true;
+        } else if (x < 0.0) {
+            x = dadd(x, M);
+            wrapped = true;
         }
+        wraps += wrapped ? 1 : 0;
         n++;
         if (n == next) {
             emit(j++, x, wraps);
@@ -301,17 +313,17 @@ GS_HD void code_chain(double x, const double d, const int n_total, const int eve
 
     // The loops are shaped so that the threads of a warp - the same satellite in 32 consecutive
     // epochs, i.e. chains that cross the binades and the wrap at nearly the same sample - take the
-    // same number of trips and re-converge once per code period: one trip of the outer loop is one
-    // code period, one trip of loop B is one binade (a jump and the real step across its edge).
-    // The vote at the top of every period keeps the warp together (threads that are done idle).
+    // same number of trips and re-converge once per period: one trip of the outer loop is one
+    // period (code period / carrier cycle), one trip of loop B is one binade (a jump and the real
+    // step across its edge).  The votes keep the warp together (threads that are done idle).
     emit(0, x, 0);
-    while (warp_any(mask, n < last)) {
-        // A: the low binades hold only a handful of samples (2^shift/1.x each): real additions
-        while (n < last && shift_of(x) < 4)
-            real_step();
-        // B: one binade per trip, until the chain wraps (shift <= 30 keeps k inside an int); the
-        // vote per trip keeps the warp on the same binade
-        bool in_period = n < last;
+    while (warp_any(mask, n < n_end)) {
+        // A: the low binades hold only a handful of steps (2^shift/1.x each): real additions
+        while (n < n_end && shift_of(x) < 4)
+            if (real_step() && neg)
+                break; // a falling chain wraps out of the low binades: continue at the top in B
+        // B: one binade per trip, until the chain wraps (shift <= 30 keeps k inside an int)
+        bool in_period = n < n_end;
         while (warp_any(mask, in_period)) {
             if (!in_period)
                 continue;
@@ -325,24 +337,52 @@ GS_HD void code_chain(double x, const double d, const int n_total, const int eve
             if (shift >= 4 && shift <= 30 && !tie_odd) {
                 const double c = dfrombits((uint64_t)bex << 52);        // 2^e
                 const double u = dfrombits((uint64_t)(bex - 52) << 52); // ulp(x)
-                const double lim = (bex == 1023 + 9) ? (double)kCaLen : dadd(c, c);
-                const double delta = dadd(dadd(c, d), -c);
-                const double top = dadd(lim, -u);  // stay strictly inside the binade / below the wrap
-                const double room = dadd(top, -x); // exact, >= 0
-                int k = (int)(room * rd);
-                double y = dfma((double)k, delta, x);
-                if (y > top) {
-                    k--;
+                int k;
+                double y, delta;
+                bool ok;
+                if (!neg) {
+                    // delta = d rounded to a multiple of ulp(x) exactly as "x + d" rounds it (ties go to
+                    // the even significand, and 2^e has an even one)
+                    delta = dadd(dadd(c, d), -c);
+                    const double c2 = dadd(c, c);
+                    const double top = dadd(c2 > M ? M : c2, -u); // strictly inside the binade, below the wrap
+                    const double room = dadd(top, -x);            // exact, >= 0
+                    k = (int)(room * rd);
                     y = dfma((double)k, delta, x);
-                } else if (dadd(top, -y) >= delta) {
-                    k++;
+                    if (y > top) {
+                        k--;
+                        y = dfma((double)k, delta, x);
+                    } else if (dadd(top, -y) >= delta) {
+                        k++;
+                        y = dfma((double)k, delta, x);
+                    }
+                    if (k > n_end - n) {
+                        k = n_end - n;
+                        y = dfma((double)k, delta, x);
+                    }
+                    ok = k > 0 && y <= top;
+                } else {
+                    // falling chain: same with 1.5*2^e as the rounding anchor (even significand, and
+                    // anchor + d stays inside the binade), down to the bottom 2^e inclusive
+                    const double c15 = dfma(0.5, c, c);
+                    delta = dadd(dadd(c15, d), -c15);      // negative
+                    const double room = dadd(x, -c);        // exact, >= 0
+                    k = (int)(room * rd);
                     y = dfma((double)k, delta, x);
+                    if (y < c) {
+                        k--;
+                        y = dfma((double)k, delta, x);
+                    } else if (dadd(y, -c) >= -delta) {
+                        k++;
+                        y = dfma((double)k, delta, x);
+                    }
+                    if (k > n_end - n) {
+                        k = n_end - n;
+                        y = dfma((double)k, delta, x);
+                    }
+                    ok = k > 0 && y >= c;
                 }
-                if (k > last - n) {
-                    k = last - n;
-                    y = dfma((double)k, delta, x);
-                }
-                if (k > 0 && y <= top) {
+                if (ok) {
                     // checkpoints that fall inside the jump
                     while (next - n <= k) {
                         emit(j++, dfma((double)(next - n), delta, x), wraps);
@@ -352,10 +392,20 @@ GS_HD void code_chain(double x, const double d, const int n_total, const int eve
                     n += k;
                 }
             }
-            if (n >= last || real_step())
+            if (n >= n_end || real_step())
                 in_period = false;
         }
     }
+    return x;
+}
+
+// K1's use: code-phase checkpoints at sample indices j*every, j = 0 .. ceil(n_total/every)-1.
+template <class Emit>
+GS_HD void code_chain(double x, const double d, const int n_total, const int every, Emit emit,
+                      const unsigned mask = 0xffffffffu)
+{
+    const int last = ((n_total - 1) / every) * every; // sample index of the last checkpoint
+    phase_chain(x, d, (double)kCaLen, last, every, emit, mask);
 }
 
 // Plain replay of the same chain (N dependent adds); kept as the in-tree cross-check of
@@ -479,6 +529,103 @@ GS_HD void synth_wrap(typename A::acc_t (&acc)[S], ChanState &st, const double d
     st.phs = phs;
 }
 
+// =====================================================================================
+// FLOAT_CARR_PHASE hosts (gpssim.h:4 as shipped): the carrier phase is a double in [0,1) that is
+// advanced by RN(f_carr*delt) per sample and wrapped both ways (gpssim.c:2245-2250), the table index
+// is floor(carr_phase*512) (gpssim.c:2200).  The device keeps cph = 512*carr_phase (an exact
+// power-of-two rescaling: every rounding commutes with it), so the index is floor(cph), again taken
+// with one round-down magic add: the low word of (cph + 2^45) is floor(cph*128) = index<<7 plus 7
+// fraction bits, i.e. already the byte offset into the replicated table once masked.
+// =====================================================================================
+constexpr double kCarrMod = 512.0;
+
+GS_HD uint32_t carrier_offset_bits(double cph) // floor(cph * 128), cph in [0, 512)
+{
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__double2loint(__dadd_rd(cph, 35184372088832.0)); // 2^45
+#else
+    return (uint32_t)(int64_t)__builtin_floor(cph * 128.0);
+#endif
+}
+GS_HD double carrier_step(double cph, const double dc) // gpssim.c:2245-2250, scaled by 512
+{
+    cph = dadd(cph, dc);
+    if (cph >= kCarrMod)
+        cph = dadd(cph, -kCarrMod);
+    else if (cph < 0.0)
+        cph = dadd(cph, kCarrMod);
+    return cph;
+}
+
+struct ChanStateF {
+    double x;      // code phase
+    double cph;    // 512 * carr_phase
+    int32_t icode; // 0..19
+    int32_t bitk;  // data bits consumed since the row
+};
+
+template <class A>
+GS_HD typename A::tab_t lut_at_f(const typename A::tab_t *lut, uint32_t fl, uint32_t t, uint32_t lane_off)
+{
+    // chip sign = half a cycle = bit 8 of the index = bit 15 of the offset; t has the chip in bit 31
+    const uint32_t off = ((fl ^ (t >> 16)) & 0xff80u) | lane_off;
+    return *reinterpret_cast<const typename A::tab_t *>(reinterpret_cast<const char *>(lut) + off);
+}
+
+template <class A, int S>
+GS_HD void synth_fast_f(typename A::acc_t (&acc)[S], ChanStateF &st, const double d, const double dc,
+                        const int signed_gain, const uint32_t *negw, const typename A::tab_t *lut,
+                        const uint32_t lane_off)
+{
+    double x = st.x, cph = st.cph;
+    const int c0 = (int)x;
+    const uint32_t win = funnel_l(negw[(c0 >> 5) + 1], negw[c0 >> 5], (uint32_t)c0 & 31u);
+    const double magic = 4503599627370496.0 - (double)c0;
+    const typename A::gain_t g = A::make_gain(signed_gain);
+#pragma unroll
+    for (int j = 0; j < S; j++) {
+        const uint32_t adv = chips_since(x, magic);
+        // (win << adv) has the current (inverted) chip in bit 31; >>16 puts it on offset bit 15
+        A::mad(acc[j], lut_at_f<A>(lut, carrier_offset_bits(cph), (win << adv) & 0x80000000u, lane_off), g);
+        x = dadd(x, d);
+        cph = carrier_step(cph, dc);
+    }
+    st.x = x;
+    st.cph = cph;
+}
+
+template <class A, int S>
+GS_HD void synth_wrap_f(typename A::acc_t (&acc)[S], ChanStateF &st, const double d, const double dc,
+                        const int32_t gain, const uint32_t nav_bits, const uint32_t *negw,
+                        const typename A::tab_t *lut, const uint32_t lane_off)
+{
+    double x = st.x, cph = st.cph;
+    const int c0 = (int)x;
+    const uint32_t win = funnel_l(negw[(c0 >> 5) + 1], negw[c0 >> 5], (uint32_t)c0 & 31u);
+    const double magic = 6755399441055744.0 - (double)c0; // 1.5 * 2^52 - c0
+    const int bit_after = st.bitk + (st.icode == 19 ? 1 : 0);
+    typename A::gain_t g = A::make_gain(data_sign(nav_bits, st.bitk) * gain);
+    const typename A::gain_t g_after = A::make_gain(data_sign(nav_bits, bit_after) * gain);
+    uint32_t wrap_off = 0;
+#pragma unroll
+    for (int j = 0; j < S; j++) {
+        const uint32_t adv = chips_since_signed(x, magic) + wrap_off;
+        A::mad(acc[j], lut_at_f<A>(lut, carrier_offset_bits(cph), (win << adv) & 0x80000000u, lane_off), g);
+        x = dadd(x, d);
+        cph = carrier_step(cph, dc);
+        const bool wrapped = x >= (double)kCaLen;
+        x = wrapped ? dadd(x, -(double)kCaLen) : x;
+        wrap_off = wrapped ? (uint32_t)kCaLen : wrap_off;
+        g = wrapped ? g_after : g;
+    }
+    if (wrap_off) {
+        st.icode = st.icode == 19 ? 0 : st.icode + 1;
+        st.bitk = bit_after;
+    }
+    st.x = x;
+    st.cph = cph;
+}
+
 // ---- output packing (gpssim.c:2258-2288) from the biased sums -------------------------
 GS_HD uint32_t pack_sc16(int32_t ib, int32_t qb) // little-endian short I, short Q
 {
@@ -556,12 +703,14 @@ GS_HD void store_run(uint8_t *dst, const typename A::acc_t (&acc)[S])
 // =====================================================================================
 struct GenericChan {
     double x, d;
-    uint32_t phs;      // carr_phase << 7
+    double cph, dc;    // FLOAT hosts: 512*carr_phase and its per-sample step
+    uint32_t phs;      // INT hosts: carr_phase << 7
     int32_t steps, gain, icode, bitk;
     uint32_t nav_bits;
     const uint32_t *negw;
 };
 
+template <bool kFloatCarrier>
 GS_HD void generic_sample(GenericChan *ch, int nc, const int16_t *sin512, const int16_t *cos512,
                           int &i16, int &q16)
 {
@@ -571,7 +720,8 @@ GS_HD void generic_sample(GenericChan *ch, int nc, const int16_t *sin512, const 
         const int chip = (int)c.x;
         const int neg = (int)((c.negw[chip >> 5] >> (31 - (chip & 31))) & 1u);
         const int sgn = (neg ? -1 : 1) * data_sign(c.nav_bits, c.bitk);
-        const int it = (int)(c.phs >> 23); // (carr_phase >> 16) & 0x1ff, gpssim.c:2202
+        // (carr_phase >> 16) & 0x1ff (gpssim.c:2202) / (int)floor(carr_phase*512) (gpssim.c:2200)
+        const int it = kFloatCarrier ? ((int)c.cph & 0x1ff) : (int)(c.phs >> 23);
         i_acc += sgn * (int)cos512[it] * c.gain;
         q_acc += sgn * (int)sin512[it] * c.gain;
         c.x = dadd(c.x, c.d);
@@ -582,7 +732,10 @@ GS_HD void generic_sample(GenericChan *ch, int nc, const int16_t *sin512, const 
                 c.bitk++;
             }
         }
-        c.phs += (uint32_t)c.steps;
+        if (kFloatCarrier)
+            c.cph = carrier_step(c.cph, c.dc);
+        else
+            c.phs += (uint32_t)c.steps;
     }
     i16 = (int)(short)((i_acc + 64) >> 7);
     q16 = (int)(short)((q_acc + 64) >> 7);

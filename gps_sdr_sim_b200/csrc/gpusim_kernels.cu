@@ -30,13 +30,33 @@ __global__ void __launch_bounds__(32) k1_chain(DeviceJob job)
     // wrap nearly in lockstep and the walk (a serial, latency-bound loop) hardly diverges.
     if (blockIdx.x == 0 && threadIdx.x == 0)
         *job.work_counter = 0; // K2 of the same job runs after this kernel on the same stream
-    const int k = blockIdx.x % kMaxChan;
-    const int e = (blockIdx.x / kMaxChan) * 32 + threadIdx.x;
+    const int groups = (job.n_epochs + 31) / 32;
+    const int blk = blockIdx.x % (groups * kMaxChan);
+    const bool carrier = blockIdx.x >= groups * kMaxChan; // FLOAT hosts: second half of the grid
+    const int k = blk % kMaxChan;
+    const int e = (blk / kMaxChan) * 32 + threadIdx.x;
     const bool has_chain = e < job.n_epochs && k < job.nch[min(e, job.n_epochs - 1)];
     const unsigned mask = __ballot_sync(0xffffffffu, has_chain);
     if (!has_chain)
         return;
     const size_t row = (size_t)e * kMaxChan + k;
+    if (carrier) {
+        // the double carrier phase of a FLOAT_CARR_PHASE host (gpssim.c:2245-2250), scaled by 512
+        double *cc = job.ck_c + row * job.kc;
+        auto emit_c = [&](int j, double x, int) { cc[j] = x; };
+        const int last = ((job.n_samples - 1) / job.chunk) * job.chunk;
+        if (kReplay) {
+            double x = job.cph0[row];
+            for (int n = 0; n <= last; n++) {
+                if (n % job.chunk == 0)
+                    cc[n / job.chunk] = x;
+                x = carrier_step(x, job.dc[row]);
+            }
+        } else {
+            phase_chain(job.cph0[row], job.dc[row], kCarrMod, last, job.chunk, emit_c, mask);
+        }
+        return;
+    }
     const double d = job.rows[row].d;
     const double x0 = job.x0[row];
     double *cx = job.ck_x + row * job.kc;
@@ -55,7 +75,7 @@ cudaError_t launch_chain(const DeviceJob &job, ChainAlgo algo, cudaStream_t stre
 {
     // Latency-bound serial chains, few of them: one warp per block spreads them over all SMs.
     const int threads = 32;
-    const int blocks = ((job.n_epochs + 31) / 32) * kMaxChan;
+    const int blocks = ((job.n_epochs + 31) / 32) * kMaxChan * (job.carrier_float ? 2 : 1);
     if (blocks == 0)
         return cudaSuccess;
     if (algo == ChainAlgo::Replay)
@@ -87,23 +107,41 @@ size_t synth_smem_bytes(int max_active, int threads)
 }
 
 // Shared-memory views of one block.  Per-thread channel state lives in shared memory (it does not
-// fit in registers next to 32 accumulators): channel k, thread t at byte k*16*T + t*8 holds the code
-// phase (f64) and 8*T bytes further the pair (carrier phase << 7, icode | bitk<<8 | signed gain<<16).
-// It is addressed with 32-bit shared-window addresses so that the per-channel address update is a
-// single integer add.
+// fit in registers next to 32 accumulators).  It is addressed with 32-bit shared-window addresses so
+// that the per-channel address update is a single integer add.  With T threads per block, channel k,
+// thread t:
+//   integer carrier: k*16T + t*8 : code phase f64 ; + 8T : (carrier phase << 7, meta)
+//   double carrier : k*24T + t*8 : code phase f64 ; + 8T : 512*carr_phase f64 ; + 16T : meta
+// meta = icode | bitk<<8 | (dataBit*gain)<<16.
 template <class A>
 struct K2Smem {
     typename A::tab_t *lut; // replicated carrier table
     uint32_t *negw;         // inverted C/A chips, [33][35]
     uint32_t state;         // shared-window address of this thread's slot for channel 0
 };
-constexpr uint32_t kStateStride = 16u * kK2Threads; // bytes between channels
-constexpr uint32_t kStatePm = 8u * kK2Threads;      // offset of the (phs, meta) pair
+constexpr int kK2ThreadsFloat = 384; // FLOAT_CARR_PHASE kernel: 24 B of state per channel and thread
+template <bool CF> struct K2Geom {
+    static constexpr int kThreads = CF ? kK2ThreadsFloat : kK2Threads;
+    static constexpr uint32_t kStride = (CF ? 24u : 16u) * kThreads; // bytes between channels
+    static constexpr uint32_t kSecond = 8u * kThreads;               // (phs, meta) / 512*carr_phase
+    static constexpr uint32_t kMeta = CF ? 16u * kThreads : 8u * kThreads + 4u;
+};
+
+size_t synth_smem_bytes_float(int max_active)
+{
+    return kSmemLut + kSmemNegw + (size_t)std::max(1, max_active) * K2Geom<true>::kStride;
+}
 
 __device__ __forceinline__ double lds_f64(uint32_t a)
 {
     double v;
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
 __device__ __forceinline__ uint2 lds_u32x2(uint32_t a)
@@ -122,57 +160,79 @@ __device__ __forceinline__ void sts_u32x2(uint32_t a, uint32_t v0, uint32_t v1)
 // SR consecutive samples of one thread, all channels, packed and stored.
 // Lanes of a warp vote per channel on whether any of them may reach the 1023-chip wrap inside
 // the run; only then the (longer) wrap-aware loop is taken for that channel.
-// rows4: this epoch's rows as uint4 pairs; cthr_mask: 0xffff, or 0 to force the wrap-aware loop.
-template <class A, int FMT, int SR>
-__device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows4, const int nc, const int ncw,
-                                          const bool live, const unsigned mask, const uint32_t lane_off,
-                                          const uint32_t cthr_mask, uint8_t *dst)
+// rows4: this epoch's rows as uint4 pairs; dcs: this epoch's carrier steps (double carrier only);
+// cthr_mask: 0xffff, or 0 to force the wrap-aware loop.
+template <class A, int FMT, int SR, bool CF>
+__device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows4, const double *dcs, const int nc,
+                                          const int ncw, const bool live, const unsigned mask,
+                                          const uint32_t lane_off, const uint32_t cthr_mask, uint8_t *dst)
 {
+    typedef K2Geom<CF> G;
     typename A::acc_t acc[SR];
 #pragma unroll
     for (int j = 0; j < SR; j++)
         acc[j] = A::init();
 
     uint32_t sa = sm.state;
-    for (int k = 0; k < ncw; k++, sa += kStateStride) {
+    for (int k = 0; k < ncw; k++, sa += G::kStride) {
         const bool act = live && k < nc;
-        ChanState st;
         uint4 r0 = make_uint4(0, 0, 0, 0);
-        uint32_t meta = 0;
+        double x = 0.0;
         bool wrap = false;
         if (act) {
             r0 = rows4[2 * k]; // d, steps, cthr | prn<<16 | gain8<<24
-            st.x = lds_f64(sa);
-            const uint2 pm = lds_u32x2(sa + kStatePm);
-            st.phs = pm.x;
-            meta = pm.y;
-            wrap = (int)st.x >= (int)(r0.w & cthr_mask);
+            x = lds_f64(sa);
+            wrap = (int)x >= (int)(r0.w & cthr_mask);
         }
         const bool any_wrap = __any_sync(mask, wrap);
         if (act) {
             const double d = __hiloint2double((int)r0.y, (int)r0.x);
-            const uint32_t steps = r0.z;
             const uint32_t *nw = sm.negw + ((r0.w >> 16) & 0xffu) * kCaWords;
-            if (!any_wrap) {
-                synth_fast<A, SR>(acc, st, d, steps, meta_sgain(meta), nw, sm.lut, lane_off);
+            if (!CF) {
+                ChanState st;
+                st.x = x;
+                const uint2 pm = lds_u32x2(sa + G::kSecond);
+                st.phs = pm.x;
+                if (!any_wrap) {
+                    synth_fast<A, SR>(acc, st, d, r0.z, meta_sgain(pm.y), nw, sm.lut, lane_off);
+                } else {
+                    const uint4 r1 = rows4[2 * k + 1]; // ph0s, gain, nav_bits, icode0 | flags<<16
+                    st.icode = meta_icode(pm.y);
+                    st.bitk = meta_bitk(pm.y);
+                    synth_wrap<A, SR>(acc, st, d, r0.z, (int32_t)r1.y, r1.z, nw, sm.lut, lane_off);
+                    sts_u32(sa + G::kMeta, pack_meta(st.icode, st.bitk, data_sign(r1.z, st.bitk) * (int32_t)r1.y));
+                }
+                sts_f64(sa, st.x);
+                sts_u32(sa + G::kSecond, st.phs);
             } else {
-                const uint4 r1 = rows4[2 * k + 1]; // ph0s, gain, nav_bits, icode0 | flags<<16
-                st.icode = meta_icode(meta);
-                st.bitk = meta_bitk(meta);
-                synth_wrap<A, SR>(acc, st, d, steps, (int32_t)r1.y, r1.z, nw, sm.lut, lane_off);
-                sts_u32(sa + kStatePm + 4, pack_meta(st.icode, st.bitk, data_sign(r1.z, st.bitk) * (int32_t)r1.y));
+                ChanStateF st;
+                st.x = x;
+                st.cph = lds_f64(sa + G::kSecond);
+                const uint32_t meta = lds_u32(sa + G::kMeta);
+                const double dc = dcs[k];
+                if (!any_wrap) {
+                    synth_fast_f<A, SR>(acc, st, d, dc, meta_sgain(meta), nw, sm.lut, lane_off);
+                } else {
+                    const uint4 r1 = rows4[2 * k + 1];
+                    st.icode = meta_icode(meta);
+                    st.bitk = meta_bitk(meta);
+                    synth_wrap_f<A, SR>(acc, st, d, dc, (int32_t)r1.y, r1.z, nw, sm.lut, lane_off);
+                    sts_u32(sa + G::kMeta, pack_meta(st.icode, st.bitk, data_sign(r1.z, st.bitk) * (int32_t)r1.y));
+                }
+                sts_f64(sa, st.x);
+                sts_f64(sa + G::kSecond, st.cph);
             }
-            sts_f64(sa, st.x);
-            sts_u32(sa + kStatePm, st.phs);
         }
     }
     if (live)
         store_run<A, FMT, SR>(dst, acc);
 }
 
-template <class A, int FMT, int S>
-__global__ void __launch_bounds__(kK2Threads, 1) k2_synth(DeviceJob job)
+template <class A, int FMT, int S, bool CF>
+__global__ void __launch_bounds__(K2Geom<CF>::kThreads, 1) k2_synth(DeviceJob job)
 {
+    typedef K2Geom<CF> G;
+    constexpr int T = G::kThreads;
     extern __shared__ __align__(16) unsigned char smem[];
     typedef typename A::tab_t tab_t;
     K2Smem<A> sm;
@@ -188,10 +248,10 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_synth(DeviceJob job)
         const tab_t *src = sizeof(tab_t) == 4 ? reinterpret_cast<const tab_t *>(job.lut_wide)
                                               : reinterpret_cast<const tab_t *>(job.lut_f32);
         constexpr int kPerEntry = 128 / (int)sizeof(tab_t);
-        for (int i = tid; i < kLutEntries * kPerEntry; i += kK2Threads)
+        for (int i = tid; i < kLutEntries * kPerEntry; i += T)
             sm.lut[i] = src[i / kPerEntry];
     }
-    for (int i = tid; i < kCaPrns * kCaWords; i += kK2Threads)
+    for (int i = tid; i < kCaPrns * kCaWords; i += T)
         sm.negw[i] = job.negw[i];
     if (tid < 32)
         lane_tab[tid] = (uint32_t)(tid & A::kLaneMask) << A::kLaneShift;
@@ -241,18 +301,24 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_synth(DeviceJob job)
             const int nrun = min(job.chunk, job.n_samples - n0);
             const DevRow *rows = job.rows + (size_t)e * kMaxChan;
             const uint4 *rows4 = reinterpret_cast<const uint4 *>(rows);
+            const double *dcs = CF ? job.dc + (size_t)e * kMaxChan : nullptr;
             const int nc = job.nch[e];
 
             // chunk-start state of every channel
             uint32_t sa = sm.state;
-            for (int k = 0; k < nc; k++, sa += kStateStride) {
+            for (int k = 0; k < nc; k++, sa += G::kStride) {
                 const size_t ck = ((size_t)e * kMaxChan + k) * job.kc + jc;
                 const DevRow r = rows[k];
                 const int ic = (int)r.icode0 + (int)job.ck_w[ck];
                 const int bitk = ic / 20;
+                const uint32_t meta = pack_meta(ic - bitk * 20, bitk, data_sign(r.nav_bits, bitk) * r.gain);
                 sts_f64(sa, job.ck_x[ck]);
-                sts_u32x2(sa + kStatePm, r.ph0s + (uint32_t)n0 * (uint32_t)r.steps,
-                          pack_meta(ic - bitk * 20, bitk, data_sign(r.nav_bits, bitk) * r.gain));
+                if (!CF) {
+                    sts_u32x2(sa + G::kSecond, r.ph0s + (uint32_t)n0 * (uint32_t)r.steps, meta);
+                } else {
+                    sts_f64(sa + G::kSecond, job.ck_c[ck]);
+                    sts_u32(sa + G::kMeta, meta);
+                }
             }
 
             // warp-wide channel and run counts: every participating lane runs the same number of loop
@@ -266,11 +332,11 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_synth(DeviceJob job)
             uint8_t *outp = job.out + (size_t)e * job.epoch_bytes + (size_t)(n0 / 8) * kBytesPer8;
 
             for (int i = 0; i < full_w; i++)
-                synth_run<A, FMT, S>(sm, rows4, nc, ncw, i < full, mask, lane_off, cthr_mask,
-                                     outp + (size_t)i * (S / 8) * kBytesPer8);
+                synth_run<A, FMT, S, CF>(sm, rows4, dcs, nc, ncw, i < full, mask, lane_off, cthr_mask,
+                                         outp + (size_t)i * (S / 8) * kBytesPer8);
             for (int i = 0; i < tail_w; i++)
-                synth_run<A, FMT, 8>(sm, rows4, nc, ncw, i < tail8, mask, lane_off, cthr_mask,
-                                     outp + ((size_t)full * (S / 8) + i) * kBytesPer8);
+                synth_run<A, FMT, 8, CF>(sm, rows4, dcs, nc, ncw, i < tail8, mask, lane_off, cthr_mask,
+                                         outp + ((size_t)full * (S / 8) + i) * kBytesPer8);
         }
         __syncwarp();
     }
@@ -279,7 +345,7 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_synth(DeviceJob job)
 // ------------------------------------------------------------------------------------
 // K2 generic
 // ------------------------------------------------------------------------------------
-template <int FMT>
+template <int FMT, bool CF>
 __global__ void __launch_bounds__(128) k2_generic(DeviceJob job)
 {
     const long long total = (long long)job.n_epochs * job.kc;
@@ -302,6 +368,8 @@ __global__ void __launch_bounds__(128) k2_generic(DeviceJob job)
         ch[k].d = r.d;
         ch[k].phs = r.ph0s + (uint32_t)n0 * (uint32_t)r.steps;
         ch[k].steps = r.steps;
+        ch[k].cph = CF ? job.ck_c[ck] : 0.0;
+        ch[k].dc = CF ? job.dc[(size_t)e * kMaxChan + k] : 0.0;
         ch[k].gain = r.gain;
         ch[k].icode = ic % 20;
         ch[k].bitk = ic / 20;
@@ -313,7 +381,7 @@ __global__ void __launch_bounds__(128) k2_generic(DeviceJob job)
     uint32_t byte = 0;
     for (int n = 0; n < nrun; n++) {
         int i16, q16;
-        generic_sample(ch, nc, job.sin16, job.cos16, i16, q16);
+        generic_sample<CF>(ch, nc, job.sin16, job.cos16, i16, q16);
         const int s = n0 + n;
         if (FMT == 16) {
             reinterpret_cast<uint32_t *>(base)[s] = ((uint32_t)i16 & 0xffffu) | ((uint32_t)q16 << 16);
@@ -331,24 +399,28 @@ __global__ void __launch_bounds__(128) k2_generic(DeviceJob job)
     }
 }
 
-template <class A, int FMT, int S>
+template <class A, int FMT, int S, bool CF>
 static cudaError_t launch_tuned_a(const DeviceJob &job, cudaStream_t stream)
 {
-    const size_t smem = synth_smem_bytes(job.max_active, kK2Threads);
-    cudaError_t err = cudaFuncSetAttribute(k2_synth<A, FMT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    constexpr int T = K2Geom<CF>::kThreads;
+    const size_t smem = kSmemLut + kSmemNegw + (size_t)std::max(1, job.max_active) * K2Geom<CF>::kStride;
+    cudaError_t err = cudaFuncSetAttribute(k2_synth<A, FMT, S, CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess)
         return err;
     const long long units = job.n_units;
-    const long long warps_per_block = kK2Threads / 32;
+    const long long warps_per_block = T / 32;
     const int blocks = (int)std::min<long long>(std::max(1, job.sm_count), (units + warps_per_block - 1) / warps_per_block);
-    k2_synth<A, FMT, S><<<blocks, kK2Threads, smem, stream>>>(job);
+    k2_synth<A, FMT, S, CF><<<blocks, T, smem, stream>>>(job);
     return cudaGetLastError();
 }
 
 template <int FMT, int S>
 static cudaError_t launch_tuned(const DeviceJob &job, cudaStream_t stream)
 {
-    return job.accum == 1 ? launch_tuned_a<AccF32x2, FMT, S>(job, stream) : launch_tuned_a<AccWide, FMT, S>(job, stream);
+    if (job.carrier_float)
+        return launch_tuned_a<AccF32x2, FMT, S, true>(job, stream);
+    return job.accum == 1 ? launch_tuned_a<AccF32x2, FMT, S, false>(job, stream)
+                          : launch_tuned_a<AccWide, FMT, S, false>(job, stream);
 }
 
 template <int FMT>
@@ -357,7 +429,10 @@ static cudaError_t launch_generic(const DeviceJob &job, cudaStream_t stream)
     const long long total = (long long)job.n_epochs * job.kc;
     const int threads = 128;
     const int blocks = (int)((total + threads - 1) / threads);
-    k2_generic<FMT><<<blocks, threads, 0, stream>>>(job);
+    if (job.carrier_float)
+        k2_generic<FMT, true><<<blocks, threads, 0, stream>>>(job);
+    else
+        k2_generic<FMT, false><<<blocks, threads, 0, stream>>>(job);
     return cudaGetLastError();
 }
 

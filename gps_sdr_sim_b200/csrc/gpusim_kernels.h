@@ -17,6 +17,9 @@ struct DeviceJob {
     const double *x0;        // [n_epochs][16] code_phase at epoch start
     double *ck_x;            // [n_epochs][16][kc] code phase at sample j*chunk
     uint16_t *ck_w;          // [n_epochs][16][kc] 1023-chip wraps before sample j*chunk
+    const double *dc;        // FLOAT hosts: [n_epochs][16] 512*RN(f_carr*delt)
+    const double *cph0;      // FLOAT hosts: [n_epochs][16] 512*carr_phase at epoch start
+    double *ck_c;            // FLOAT hosts: [n_epochs][16][kc] 512*carr_phase at sample j*chunk
     const int32_t *lut_wide; // [512] AccWide::table_entry(cos, sin)
     const uint64_t *lut_f32; // [512] AccF32x2::table_entry(cos, sin)
     const int16_t *sin16;    // [512] plain tables for the generic kernel
@@ -37,6 +40,7 @@ struct DeviceJob {
     int32_t ppe;             // aligned layout: code periods per epoch (100), chunk = period / q; 0 = plain
     int32_t q;               // aligned layout: chunks per code period
     int32_t n_units;         // work units (32 chunks each) of the tuned kernel
+    int32_t carrier_float;   // 1: FLOAT_CARR_PHASE host (double carrier phase), 0: integer carrier
 };
 
 enum class ChainAlgo { Jump = 0, Replay = 1 };

@@ -14,6 +14,7 @@
 
 #include "gpusim.h"
 #include "gpusim_tables.h"
+#include "gpusim_core.h"
 
 namespace gpusim {
 
@@ -127,6 +128,17 @@ uint32_t gpusim_pack_nav_bits(const unsigned long *dwrd, int32_t n_dwrd, int32_t
         out |= (uint32_t)((dwrd[w] >> (29 - b)) & 1UL) << (31 - k);
     }
     return out;
+}
+
+// N executions of the FLOAT_CARR_PHASE carrier update (gpssim.c:2245-2250) in O(carrier cycles)
+// instead of O(N): the same exact binade walk the device uses, on the host.
+double gpusim_advance_carrier_f64(double carr_phase, double f_carr, double delt, int32_t n_samples)
+{
+    const volatile double d = f_carr * delt;
+    if (n_samples <= 0 || d == 0.0)
+        return carr_phase;
+    auto nothing = [](int, double, int) {};
+    return gpusim::phase_chain(carr_phase * 512.0, (double)d * 512.0, 512.0, n_samples, 1 << 30, nothing) / 512.0;
 }
 
 } // extern "C"

@@ -177,6 +177,13 @@ int gpusim_ca_code(int32_t prn, int32_t *ca1023);
  * (gpssim.h:175, unsigned long on the host) into the nav_bits row format. */
 uint32_t gpusim_pack_nav_bits(const unsigned long *dwrd, int32_t n_dwrd, int32_t iword, int32_t ibit);
 
+/*
+ * FLOAT_CARR_PHASE hosts only: the value of chan[i].carr_phase after n_samples executions of
+ * "carr_phase += f_carr*delt; wrap into [0,1)" (gpssim.c:2245-2250) - what the removed sample loop
+ * left behind for the next epoch - computed exactly in O(carrier cycles).  Host-side, no GPU needed.
+ */
+double gpusim_advance_carrier_f64(double carr_phase, double f_carr, double delt, int32_t n_samples);
+
 #ifdef __cplusplus
 }
 #endif

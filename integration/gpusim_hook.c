@@ -238,22 +238,9 @@ void gpusim_hook_epoch(gpusim_hook *h, channel_t *chan, const int *gain)
 		b->carr_phasestep[o] = 0;
 		b->carr_phase[o] = 0;
 		b->carr_phase_f[o] = chan[i].carr_phase;
-		{
-			/* The double carrier phase chains through every sample of every epoch
-			 * (gpssim.c:2245-2250); keep the host's copy exact by replaying it. */
-			double cp = chan[i].carr_phase;
-			const double dcp = chan[i].f_carr * h->delt;
-			int n;
-			for (n = 0; n < h->N; n++)
-			{
-				cp += dcp;
-				if (cp >= 1.0)
-					cp -= 1.0;
-				else if (cp < 0.0)
-					cp += 1.0;
-			}
-			chan[i].carr_phase = cp;
-		}
+		/* The double carrier phase chains through every sample of every epoch (gpssim.c:2245-2250);
+		 * keep the host's copy exact: the library walks the N updates in O(carrier cycles). */
+		chan[i].carr_phase = gpusim_advance_carrier_f64(chan[i].carr_phase, chan[i].f_carr, h->delt, h->N);
 #else
 		b->carr_phasestep[o] = chan[i].carr_phasestep;
 		b->carr_phase[o] = chan[i].carr_phase;

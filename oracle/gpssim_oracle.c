@@ -322,3 +322,28 @@ void oracle_code_phase_checkpoints(double code_phase, double f_code, double delt
 		}
 	}
 }
+
+/*
+ * The double carrier-phase recurrence alone (FLOAT_CARR_PHASE branch, gpssim.c:2244-2250), for
+ * checking the device's carrier checkpoint chain: writes carr_phase at every sample index that is a
+ * multiple of `every` and returns the value after N samples (what the next epoch starts from).
+ */
+double oracle_carrier_phase_checkpoints(double carr_phase, double f_carr, double delt, int N, int every,
+                                        double *x_out)
+{
+	int n;
+	for (n = 0; n < N; n++)
+	{
+		if (n % every == 0)
+			x_out[n / every] = carr_phase;
+		{
+			volatile double inc = f_carr * delt;
+			carr_phase += inc;
+		}
+		if (carr_phase >= 1.0)
+			carr_phase -= 1.0;
+		else if (carr_phase < 0.0)
+			carr_phase += 1.0;
+	}
+	return carr_phase;
+}

@@ -94,9 +94,62 @@ void tuned_chunk(const Tables &T, const DevRow *rows, int nc, const double *ckx,
         emu_run<A, FMT, 8>(T, rows, nc, st, meta, force_wrap, lane_off, outp + ((size_t)full * (S / 8) + i) * kBytesPer8);
 }
 
-template <int FMT>
-void generic_chunk(const Tables &T, const DevRow *rows, int nc, const double *ckx, const uint16_t *ckw, int kc,
-                   int jc, int chunk, int N, uint8_t *base)
+// ---- FLOAT_CARR_PHASE (double carrier phase) variants ---------------------------------------------
+template <class A, int FMT, int SR>
+void emu_run_f(const Tables &T, const DevRow *rows, const double *dcs, int nc, ChanStateF *st, uint32_t *meta,
+               int force_wrap, uint32_t lane_off, uint8_t *dst)
+{
+    const typename A::tab_t *lut = table_of<A>(T);
+    typename A::acc_t acc[SR];
+    for (int j = 0; j < SR; j++)
+        acc[j] = A::init();
+    for (int k = 0; k < nc; k++) {
+        const DevRow &r = rows[k];
+        const bool wrap = (int)st[k].x >= (int)r.cthr || force_wrap;
+        const uint32_t *nw = T.negw.data() + (size_t)r.prn * kCaWords;
+        if (!wrap) {
+            synth_fast_f<A, SR>(acc, st[k], r.d, dcs[k], meta_sgain(meta[k]), nw, lut, lane_off);
+        } else {
+            st[k].icode = meta_icode(meta[k]);
+            st[k].bitk = meta_bitk(meta[k]);
+            synth_wrap_f<A, SR>(acc, st[k], r.d, dcs[k], r.gain, r.nav_bits, nw, lut, lane_off);
+            meta[k] = pack_meta(st[k].icode, st[k].bitk, data_sign(r.nav_bits, st[k].bitk) * r.gain);
+        }
+    }
+    store_run<A, FMT, SR>(dst, acc);
+}
+
+template <int FMT, int S>
+void tuned_chunk_f(const Tables &T, const DevRow *rows, const double *dcs, int nc, const double *ckx,
+                   const uint16_t *ckw, const double *ckc, int kc, int jc, int chunk, int N, int force_wrap,
+                   int lane, uint8_t *epoch_out)
+{
+    typedef AccF32x2 A;
+    const int n0 = jc * chunk;
+    const int nrun = std::min(chunk, N - n0);
+    ChanStateF st[kMaxChan];
+    uint32_t meta[kMaxChan];
+    for (int k = 0; k < nc; k++) {
+        const int ic = rows[k].icode0 + ckw[k * kc + jc];
+        const int bitk = ic / 20;
+        st[k].x = ckx[k * kc + jc];
+        st[k].cph = ckc[k * kc + jc];
+        meta[k] = pack_meta(ic - bitk * 20, bitk, data_sign(rows[k].nav_bits, bitk) * rows[k].gain);
+    }
+    constexpr int kBytesPer8 = (FMT == 16) ? 32 : (FMT == 8) ? 16 : 2;
+    uint8_t *outp = epoch_out + (size_t)(n0 / 8) * kBytesPer8;
+    const uint32_t lane_off = (uint32_t)(lane & A::kLaneMask) << A::kLaneShift;
+    const int full = nrun / S, tail8 = (nrun - full * S) / 8;
+    for (int i = 0; i < full; i++)
+        emu_run_f<A, FMT, S>(T, rows, dcs, nc, st, meta, force_wrap, lane_off, outp + (size_t)i * (S / 8) * kBytesPer8);
+    for (int i = 0; i < tail8; i++)
+        emu_run_f<A, FMT, 8>(T, rows, dcs, nc, st, meta, force_wrap, lane_off,
+                             outp + ((size_t)full * (S / 8) + i) * kBytesPer8);
+}
+
+template <int FMT, bool CF>
+void generic_chunk(const Tables &T, const DevRow *rows, const double *dcs, int nc, const double *ckx,
+                   const uint16_t *ckw, const double *ckc, int kc, int jc, int chunk, int N, uint8_t *base)
 {
     const int n0 = jc * chunk;
     const int nrun = std::min(chunk, N - n0);
@@ -108,6 +161,8 @@ void generic_chunk(const Tables &T, const DevRow *rows, int nc, const double *ck
         ch[k].d = r.d;
         ch[k].phs = r.ph0s + (uint32_t)n0 * (uint32_t)r.steps;
         ch[k].steps = r.steps;
+        ch[k].cph = CF ? ckc[k * kc + jc] : 0.0;
+        ch[k].dc = CF ? dcs[k] : 0.0;
         ch[k].gain = r.gain;
         ch[k].icode = ic % 20;
         ch[k].bitk = ic / 20;
@@ -117,7 +172,7 @@ void generic_chunk(const Tables &T, const DevRow *rows, int nc, const double *ck
     uint32_t byte = 0;
     for (int n = 0; n < nrun; n++) {
         int i16, q16;
-        generic_sample(ch, nc, T.s16.data(), T.c16.data(), i16, q16);
+        generic_sample<CF>(ch, nc, T.s16.data(), T.c16.data(), i16, q16);
         const int s = n0 + n;
         if (FMT == 16) {
             const uint32_t w = ((uint32_t)i16 & 0xffffu) | ((uint32_t)q16 << 16);
@@ -143,7 +198,7 @@ extern "C" {
 // kernel: 0 = tuned S=32, 1 = tuned S=16, 2 = generic.  Returns 0, or -1 if the table is outside
 // the selected kernel's documented ranges.
 int emu_generate(const gpusim_epoch_table *t, int N, double delt, int fmt, int chunk, int kernel,
-                 int force_wrap, int chain_replay, int accum, uint8_t *out)
+                 int force_wrap, int chain_replay, int accum, int carrier_float, uint8_t *out)
 {
     static const Tables T;
     const size_t eb = fmt == 1 ? (size_t)(N / 4) : fmt == 8 ? (size_t)2 * N : (size_t)4 * N;
@@ -153,9 +208,11 @@ int emu_generate(const gpusim_epoch_table *t, int N, double delt, int fmt, int c
         return -1;
     std::vector<double> ckx((size_t)kMaxChan * kc);
     std::vector<uint16_t> ckw((size_t)kMaxChan * kc);
+    std::vector<double> ckc((size_t)kMaxChan * kc);
     for (int e = 0; e < t->n_epochs; e++) {
         DevRow rows[kMaxChan];
         double x0[kMaxChan];
+        double dcs[kMaxChan] = {0}, cph0[kMaxChan] = {0};
         int nc = 0;
         for (int i = 0; i < kMaxChan; i++) {
             const size_t r = (size_t)e * kMaxChan + i;
@@ -163,12 +220,16 @@ int emu_generate(const gpusim_epoch_table *t, int N, double delt, int fmt, int c
                 continue;
             DevRow &o = rows[nc];
             o.d = dmul(t->f_code[r], delt);
-            o.steps = (int32_t)((uint32_t)t->carr_phasestep[r] << 7);
+            o.steps = carrier_float ? 0 : (int32_t)((uint32_t)t->carr_phasestep[r] << 7);
             o.cthr = wrap_threshold(o.d);
             o.prn = (uint8_t)t->prn[r];
             o.gain = t->gain[r];
             o.gain8 = (uint8_t)o.gain;
-            o.ph0s = t->carr_phase[r] << 7;
+            o.ph0s = carrier_float ? 0u : t->carr_phase[r] << 7;
+            if (carrier_float) {
+                dcs[nc] = dmul(t->f_carr[r], delt) * 512.0;
+                cph0[nc] = t->carr_phase_f[r] * 512.0;
+            }
             o.nav_bits = t->nav_bits[r];
             o.icode0 = (uint16_t)t->icode[r];
             o.flags = 0;
@@ -187,24 +248,44 @@ int emu_generate(const gpusim_epoch_table *t, int N, double delt, int fmt, int c
                 code_chain_replay(x0[k], rows[k].d, N, chunk, emit);
             else
                 code_chain(x0[k], rows[k].d, N, chunk, emit);
+            if (carrier_float) {
+                double *cc = ckc.data() + (size_t)k * kc;
+                auto emit_c = [&](int j, double x, int) { cc[j] = x; };
+                const int last = ((N - 1) / chunk) * chunk;
+                if (chain_replay) {
+                    double x = cph0[k];
+                    for (int n = 0; n <= last; n++) {
+                        if (n % chunk == 0)
+                            cc[n / chunk] = x;
+                        x = carrier_step(x, dcs[k]);
+                    }
+                } else {
+                    phase_chain(cph0[k], dcs[k], kCarrMod, last, chunk, emit_c);
+                }
+            }
         }
         uint8_t *eo = out + (size_t)e * eb;
         for (int jc = 0; jc < kc; jc++) {
             const int lane = jc & 31;
 #define EMU_TUNED(F, S)                                                                                          \
     do {                                                                                                         \
-        if (accum == 1) tuned_chunk<AccF32x2, F, S>(T, rows, nc, ckx.data(), ckw.data(), kc, jc, chunk, N, force_wrap, lane, eo); \
+        if (carrier_float) tuned_chunk_f<F, S>(T, rows, dcs, nc, ckx.data(), ckw.data(), ckc.data(), kc, jc, chunk, N, force_wrap, lane, eo); \
+        else if (accum == 1) tuned_chunk<AccF32x2, F, S>(T, rows, nc, ckx.data(), ckw.data(), kc, jc, chunk, N, force_wrap, lane, eo); \
         else tuned_chunk<AccWide, F, S>(T, rows, nc, ckx.data(), ckw.data(), kc, jc, chunk, N, force_wrap, lane, eo);            \
+    } while (0)
+#define EMU_GENERIC(F)                                                                                           \
+    do {                                                                                                         \
+        if (carrier_float) generic_chunk<F, true>(T, rows, dcs, nc, ckx.data(), ckw.data(), ckc.data(), kc, jc, chunk, N, eo); \
+        else generic_chunk<F, false>(T, rows, dcs, nc, ckx.data(), ckw.data(), ckc.data(), kc, jc, chunk, N, eo); \
     } while (0)
             if (kernel == 0) {
                 if (fmt == 16) EMU_TUNED(16, 32); else if (fmt == 8) EMU_TUNED(8, 32); else EMU_TUNED(1, 32);
             } else if (kernel == 1) {
                 if (fmt == 16) EMU_TUNED(16, 16); else if (fmt == 8) EMU_TUNED(8, 16); else EMU_TUNED(1, 16);
             } else {
-                if (fmt == 16) generic_chunk<16>(T, rows, nc, ckx.data(), ckw.data(), kc, jc, chunk, N, eo);
-                else if (fmt == 8) generic_chunk<8>(T, rows, nc, ckx.data(), ckw.data(), kc, jc, chunk, N, eo);
-                else generic_chunk<1>(T, rows, nc, ckx.data(), ckw.data(), kc, jc, chunk, N, eo);
+                if (fmt == 16) EMU_GENERIC(16); else if (fmt == 8) EMU_GENERIC(8); else EMU_GENERIC(1);
             }
+#undef EMU_GENERIC
 #undef EMU_TUNED
         }
     }
@@ -222,6 +303,17 @@ void emu_code_chain(double x0, double d, int n_total, int every, int replay, dou
         code_chain_replay(x0, d, n_total, every, emit);
     else
         code_chain(x0, d, n_total, every, emit);
+}
+
+// the generic walk:  x += d; wrap into [0, M)  for n_end steps; checkpoints every `every` steps;
+// returns the final value
+double emu_phase_chain(double x0, double d, double M, int n_end, int every, double *x_out, int *w_out)
+{
+    auto emit = [&](int j, double x, int wraps) {
+        x_out[j] = x;
+        w_out[j] = wraps;
+    };
+    return phase_chain(x0, d, M, n_end, every, emit);
 }
 
 } // extern "C"

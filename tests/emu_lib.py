@@ -33,10 +33,13 @@ def lib() -> ctypes.CDLL:
         _lib = ctypes.CDLL(build())
         _lib.emu_generate.restype = ctypes.c_int
         _lib.emu_generate.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int,
-                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         _lib.emu_code_chain.restype = None
         _lib.emu_code_chain.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_void_p]
+        _lib.emu_phase_chain.restype = ctypes.c_double
+        _lib.emu_phase_chain.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_void_p, ctypes.c_void_p]
     return _lib
 
 
@@ -45,7 +48,7 @@ def generate(table, chunk: int = 512, kernel: int = TUNED32, force_wrap: bool = 
     out = np.zeros(table.n_epochs * table.epoch_bytes, dtype=np.uint8)
     c = table.as_c()
     rc = lib().emu_generate(ctypes.addressof(c), table.samples_per_epoch, table.delt, table.data_format, chunk,
-                            kernel, int(force_wrap), int(chain_replay), accum, out.ctypes.data)
+                            kernel, int(force_wrap), int(chain_replay), accum, int(table.carrier_mode), out.ctypes.data)
     if rc != 0:
         raise ValueError("table outside the selected kernel's ranges")
     return out
@@ -57,3 +60,12 @@ def code_chain(x0: float, d: float, n: int, every: int, replay: bool = False):
     w = np.empty(k, dtype=np.int32)
     lib().emu_code_chain(x0, d, n, every, int(replay), x.ctypes.data, w.ctypes.data)
     return x, w
+
+
+def phase_chain(x0: float, d: float, modulus: float, n_end: int, every: int):
+    """(checkpoints at j*every <= n_end, wraps, final value) of the generic exact walk."""
+    k = n_end // every + 1
+    x = np.empty(k, dtype=np.float64)
+    w = np.empty(k, dtype=np.int32)
+    end = lib().emu_phase_chain(x0, d, modulus, n_end, every, x.ctypes.data, w.ctypes.data)
+    return x, w, end

@@ -41,6 +41,11 @@ SCENARIOS = {
     "static_int_b1": ("int", STATIC + ["-d", "2", "-s", "2600000", "-b", "1"], None),
     # the reference exactly as shipped (FLOAT_CARR_PHASE): pins the oracle's double-carrier branch
     "static_float_b16": ("float", STATIC + ["-d", "1", "-s", "2600000", "-b", "16"], None),
+    "circle_float_b8": ("float", ["-u", os.path.join(DATA, "circle.csv"), "-s", "2600000", "-b", "8", "-d", "1.0"], None),
+    "nmea_float_1msps_b1": ("float", ["-g", os.path.join(DATA, "triumphv3.txt"), "-s", "1000000", "-b", "1", "-d", "1.5"], None),
+    # spacecraft: +-40 kHz Doppler, i.e. both signs of a large double carrier step
+    "satellite_float_b16": ("float", ["-u", os.path.join(DATA, "satellite.csv"), "-i", "-s", "2600000", "-b", "16", "-d", "31"],
+                            [0, 1, 2, 299, 300, 301]),
     # BASELINE config 4: NMEA trajectory, 1 MS/s (more than one chip per sample), 1-bit
     "nmea_int_1msps_b1": ("int", ["-g", os.path.join(DATA, "triumphv3.txt"), "-s", "1000000", "-b", "1", "-d", "3"], None),
     # BASELINE config 2: circle.csv user motion, 8-bit

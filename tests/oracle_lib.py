@@ -35,6 +35,9 @@ def lib() -> ctypes.CDLL:
                                                        ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                                        ctypes.c_void_p]
         _lib.oracle_ca_code.restype = ctypes.c_int
+        _lib.oracle_carrier_phase_checkpoints.restype = ctypes.c_double
+        _lib.oracle_carrier_phase_checkpoints.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                                          ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     return _lib
 
 
@@ -58,6 +61,13 @@ def code_phase_checkpoints(code_phase: float, f_code: float, delt: float, n: int
     w = np.empty(k, dtype=np.int32)
     lib().oracle_code_phase_checkpoints(code_phase, f_code, delt, n, every, x.ctypes.data, w.ctypes.data)
     return x, w
+
+
+def carrier_phase_checkpoints(carr_phase: float, f_carr: float, delt: float, n: int, every: int):
+    k = (n + every - 1) // every
+    x = np.empty(k, dtype=np.float64)
+    end = lib().oracle_carrier_phase_checkpoints(carr_phase, f_carr, delt, n, every, x.ctypes.data)
+    return x, end
 
 
 def carrier_lut():

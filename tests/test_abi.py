@@ -54,10 +54,17 @@ def test_bad_config_rejected_before_touching_cuda():
     assert e.value.status == 1
 
 
-def test_float_carrier_hosts_are_refused_not_approximated():
-    with pytest.raises(gs.GpuSimError) as e:
-        gs.GpuSim(260000, 1 / 2.6e6, carrier_mode=gs.CARRIER_FLOAT)
-    assert e.value.status == 5 and "FLOAT_CARR_PHASE" in str(e.value)
+def test_exact_host_carrier_advance_matches_sequential_replay():
+    # FLOAT_CARR_PHASE hosts: gpusim_advance_carrier_f64 == N executions of gpssim.c:2245-2250
+    import numpy as np
+    import oracle_lib
+    rng = np.random.default_rng(5)
+    for f_carr in (3712.5, -3712.5, 43917.0, -40316.0, 0.0, 7.25):
+        x0 = float(rng.uniform(0, 1))
+        for fs, n in ((2.6e6, 260000), (1.0e6, 100000)):
+            _, want = oracle_lib.carrier_phase_checkpoints(x0, f_carr, 1.0 / fs, n, n)
+            got = gs.advance_carrier_f64(x0, f_carr, 1.0 / fs, n)
+            assert np.float64(got).view(np.uint64) == np.float64(want).view(np.uint64), (f_carr, fs)
 
 
 @pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")

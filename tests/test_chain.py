@@ -53,3 +53,31 @@ def test_replay_variant_matches_too():
     xo, wo = oracle_lib.code_phase_checkpoints(x0, f_code, delt, n, 512)
     xr, wr = emu_lib.code_chain(x0, d, n, 512, replay=True)
     assert np.array_equal(xo.view(np.uint64), xr.view(np.uint64)) and np.array_equal(wo, wr)
+
+
+def _carrier_cases():
+    rng = np.random.default_rng(99)
+    cases = []
+    for fs, n in ((1.0e6, 100000), (2.6e6, 260000), (20.0e6, 2000000)):
+        for f_carr in (3712.5, -3712.5, 41234.25, -40316.0, 12.75, -0.5, 1500.0 * rng.uniform(0.1, 2.0)):
+            cases.append((rng.uniform(0.0, 1.0), f_carr, 1.0 / fs, n))
+        cases.append((0.0, 2500.0, 1.0 / fs, n))
+        cases.append((np.nextafter(1.0, 0.0), -2500.0, 1.0 / fs, n))
+        cases.append((2.0 ** -40, -3000.0, 1.0 / fs, n))
+    return cases
+
+
+@pytest.mark.parametrize("x0,f_carr,delt,n", _carrier_cases())
+def test_carrier_chain_equals_sequential_replay(x0, f_carr, delt, n):
+    """FLOAT_CARR_PHASE: x += f_carr*delt with wrap into [0,1) both ways (gpssim.c:2245-2250); the device
+    walks 512*x with step 512*RN(f_carr*delt) and modulus 512 - an exact power-of-two rescaling."""
+    d = float(np.float64(f_carr) * np.float64(delt))
+    for every in (200, 520):
+        xo, end_o = oracle_lib.carrier_phase_checkpoints(x0, f_carr, delt, n, every)
+        last = ((n - 1) // every) * every
+        xj, wj, end_j = emu_lib.phase_chain(512.0 * x0, 512.0 * d, 512.0, last, every)
+        assert np.array_equal((xo * 512.0).view(np.uint64), xj[:xo.size].view(np.uint64)), every
+    # whole-epoch advance (what the host needs for the next epoch's row)
+    _, end_o = oracle_lib.carrier_phase_checkpoints(x0, f_carr, delt, n, n)
+    _, _, end_j = emu_lib.phase_chain(512.0 * x0, 512.0 * d, 512.0, n, 1 << 30)
+    assert np.float64(end_o * 512.0).view(np.uint64) == np.float64(end_j).view(np.uint64)

@@ -41,10 +41,10 @@ def _kernel_for(table):
     return emu_lib.TUNED32 if d_max <= 0.9999 else emu_lib.TUNED16
 
 
-@pytest.mark.parametrize("name", [n for n in golden_names() if "float" not in n])
+@pytest.mark.parametrize("name", golden_names())
 def test_device_algorithms_on_cpu_reproduce_reference_bytes(name):
     table, want, _ = load_golden(name)
-    assert table.carrier_mode != CARRIER_FLOAT
+    assert (table.carrier_mode == CARRIER_FLOAT) == ("float" in name)
     if table.samples_per_epoch > 300000:
         table = table.slice(0, 1)
         want = want[:1]
@@ -52,7 +52,8 @@ def test_device_algorithms_on_cpu_reproduce_reference_bytes(name):
     assert digests(out, table) == want
 
 
-@pytest.mark.parametrize("name", ["static_int_b16", "static_int_b8", "static_int_b1", "satellite_int_b16"])
+@pytest.mark.parametrize("name", ["static_int_b16", "static_int_b8", "static_int_b1", "satellite_int_b16",
+                                  "static_float_b16", "satellite_float_b16", "circle_float_b8"])
 @pytest.mark.parametrize("variant", ["wrap_path", "generic", "tuned16", "replay_chain", "chunk128", "chunk2048"])
 def test_device_algorithm_variants_agree(name, variant):
     table, want, _ = load_golden(name)

@@ -13,6 +13,7 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 HOST = os.path.join(ROOT, "integration", "_build", "gps-sdr-sim-gpu-int")
+HOST_FLOAT = os.path.join(ROOT, "integration", "_build", "gps-sdr-sim-gpu-float")
 D = oracle_lib.ref_data
 
 CASES = {
@@ -42,3 +43,29 @@ def test_host_with_gpu_binding_equals_reference_cli(name, gpu_required, tmp_path
     assert filecmp.cmp(a, b, shallow=False)
     # the CLI's own messages are untouched (gpssim.c:2037-2039, :2357)
     assert "Start time" in g.stderr and "Done!" in g.stderr
+
+
+FLOAT_CASES = {
+    "asshipped_static_b16": ["-l", "30.286502,120.032669,100", "-d", "10", "-s", "2600000", "-b", "16"],
+    "asshipped_circle_b8": ["-u", "circle.csv", "-s", "2600000", "-b", "8", "-d", "35"],
+    "asshipped_rocket_b1": ["-u", "rocket.csv", "-i", "-s", "2600000", "-b", "1", "-d", "8"],
+}
+
+
+@pytest.mark.parametrize("name", sorted(FLOAT_CASES))
+def test_asshipped_float_host_with_gpu_binding_equals_reference_cli(name, gpu_required, tmp_path):
+    """The reference exactly as shipped (FLOAT_CARR_PHASE, what `make` builds) against the same host with
+    the libgpusim binding: double carrier phase on the device, exact host-side carrier advance."""
+    ref = oracle_lib.ref_binary("float")
+    if ref is None or not os.path.exists(HOST_FLOAT):
+        pytest.skip("oracle/_ref / integration/_build were not shipped to this box")
+    argv = [D(a) if a.endswith((".csv", ".txt")) else a for a in FLOAT_CASES[name]]
+    common = ["-e", D("brdc3540.14n"), *argv]
+    a, b = tmp_path / "ref.bin", tmp_path / "gpu.bin"
+    r = subprocess.run([ref, *common, "-o", str(a)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-500:]
+    g = subprocess.run([HOST_FLOAT, *common, "-o", str(b)], capture_output=True, text=True,
+                       env=dict(os.environ, GPUSIM_BATCH_EPOCHS="100"))
+    assert g.returncode == 0, g.stderr[-800:]
+    assert os.path.getsize(a) == os.path.getsize(b) > 0
+    assert filecmp.cmp(a, b, shallow=False)

@@ -11,7 +11,7 @@ from conftest import golden_names, load_golden
 
 pytestmark = pytest.mark.gpu
 
-INT_GOLDEN = [n for n in golden_names() if "float" not in n]
+ALL_GOLDEN = golden_names()     # integer-carrier and FLOAT_CARR_PHASE hosts
 
 
 def digests(buf, table):
@@ -25,7 +25,7 @@ def _gpu(gpu_required):
     assert lib.gpusim_abi_version() == 1
 
 
-@pytest.mark.parametrize("name", INT_GOLDEN)
+@pytest.mark.parametrize("name", ALL_GOLDEN)
 def test_cuda_reproduces_reference_bytes(name):
     table, want, head = load_golden(name)
     with gs.GpuSim.for_table(table) as sim:
@@ -40,7 +40,8 @@ def test_cuda_reproduces_reference_bytes(name):
 
 
 @pytest.mark.parametrize("name", ["static_int_b16", "static_int_b8", "static_int_b1", "nmea_int_1msps_b1",
-                                  "satellite_int_b16"])
+                                  "satellite_int_b16", "static_float_b16", "nmea_float_1msps_b1",
+                                  "satellite_float_b16"])
 @pytest.mark.parametrize("opts", [{"force_slow": 1}, {"force_generic": 1}, {"chain_replay": 1}, {"accum": 0},
                                   {"layout": 1}, {"layout": 1, "chunk": 128}, {"layout": 1, "chunk": 2048},
                                   {"layout": 1, "chunk": 96, "accum": 0}, {"layout": 1, "force_slow": 1}])

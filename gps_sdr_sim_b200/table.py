@@ -126,11 +126,12 @@ class EpochTable:
 
 
 def synthetic_table(n_epochs: int, samples_per_epoch: int = 260000, n_active: int = 13,
-                    data_format: int = SC16, seed: int = 20141220) -> EpochTable:
+                    data_format: int = SC16, seed: int = 20141220, carrier_mode: int = CARRIER_INT) -> EpochTable:
     """Seeded synthetic rows inside the envelopes measured on the reference's own
     scenarios: every slot keeps its PRN for the whole
     table, the code phase and carrier phase are continuous from epoch to epoch the
-    way the host produces them, Doppler drifts slowly.  Integer-carrier mode."""
+    way the host produces them, Doppler drifts slowly.  carrier_mode=CARRIER_FLOAT fills the double
+    carrier columns the way a FLOAT_CARR_PHASE host does (exact per-epoch advance)."""
     rng = np.random.default_rng(seed)
     N = int(samples_per_epoch)
     fs = 10.0 * N
@@ -171,4 +172,10 @@ def synthetic_table(n_epochs: int, samples_per_epoch: int = 260000, n_active: in
         cols["carr_phasestep"][:, s] = step.astype(np.int32)
         cols["carr_phase"][:, s] = ph.astype(np.uint32)
         cols["f_carr"][:, s] = f_carr
-    return EpochTable(N, delt, data_format, CARRIER_INT, cols)
+        if carrier_mode == CARRIER_FLOAT:
+            from .api import advance_carrier_f64
+            cph = float(rng.uniform(0.0, 1.0))
+            for e in range(E):
+                cols["carr_phase_f"][e, s] = cph
+                cph = advance_carrier_f64(cph, float(f_carr[e]), delt, N)
+    return EpochTable(N, delt, data_format, carrier_mode, cols)

@@ -12,7 +12,8 @@ fmt = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 accum = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 E = int(sys.argv[3]) if len(sys.argv) > 3 else 600
 chunk = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-t = gs.synthetic_table(E, 260000, 13, fmt)
+mode = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+t = gs.synthetic_table(E, 260000, 13, fmt, carrier_mode=mode)
 out = torch.empty(t.n_epochs * t.epoch_bytes, dtype=torch.uint8, device="cuda")
 with gs.GpuSim.for_table(t) as sim:
     sim.set_option("accum", accum)
@@ -21,5 +22,5 @@ with gs.GpuSim.for_table(t) as sim:
     for _ in range(3):
         sim.generate_device(0, E, out.data_ptr(), out.numel())
         tm = sim.timing()
-    print(f"fmt={fmt} accum={accum} epochs={E} chunk={chunk} k1={tm.chain_ms:.3f} ms k2={tm.synth_ms:.3f} ms "
+    print(f"carrier_mode={mode} fmt={fmt} accum={accum} epochs={E} chunk={chunk} k1={tm.chain_ms:.3f} ms k2={tm.synth_ms:.3f} ms "
           f"{E * 260000 / tm.synth_ms / 1e6:.1f} GS/s")

@@ -16,7 +16,8 @@ from . import build as _build
 from .table import CEpochTable, EpochTable, epoch_bytes
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libgpusim.so")
+# GPUSIM_LIB: load another build of the same library (kernel experiments); default = the in-tree build
+_LIB_PATH = os.environ.get("GPUSIM_LIB") or os.path.join(_HERE, "libgpusim.so")
 _lib = None
 
 
@@ -46,6 +47,7 @@ EXPORTS = (
     "gpusim_epoch_bytes", "gpusim_generate_epochs", "gpusim_generate_epochs_to_sink",
     "gpusim_upload_table", "gpusim_generate_device", "gpusim_get_timing", "gpusim_set_option",
     "gpusim_carrier_lut", "gpusim_ca_code", "gpusim_pack_nav_bits", "gpusim_advance_carrier_f64",
+    "gpusim_host_alloc", "gpusim_host_free",
 )
 
 
@@ -93,6 +95,10 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.gpusim_ca_code.argtypes = [i32, vp]
     lib.gpusim_pack_nav_bits.restype = ctypes.c_uint32
     lib.gpusim_pack_nav_bits.argtypes = [vp, i32, i32, i32]
+    lib.gpusim_host_alloc.restype = vp
+    lib.gpusim_host_alloc.argtypes = [sz]
+    lib.gpusim_host_free.restype = None
+    lib.gpusim_host_free.argtypes = [vp]
     lib.gpusim_advance_carrier_f64.restype = ctypes.c_double
     lib.gpusim_advance_carrier_f64.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_double, i32]
     _lib = lib

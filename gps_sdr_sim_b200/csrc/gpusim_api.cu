@@ -252,6 +252,20 @@ extern "C" {
 
 int gpusim_abi_version(void) { return GPUSIM_ABI_VERSION; }
 
+void *gpusim_host_alloc(size_t n_bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, n_bytes ? n_bytes : 1) != cudaSuccess)
+        return nullptr;
+    return p;
+}
+
+void gpusim_host_free(void *p)
+{
+    if (p)
+        cudaFreeHost(p);
+}
+
 const char *gpusim_strerror(int status)
 {
     switch (status) {

@@ -177,6 +177,11 @@ int gpusim_ca_code(int32_t prn, int32_t *ca1023);
  * (gpssim.h:175, unsigned long on the host) into the nav_bits row format. */
 uint32_t gpusim_pack_nav_bits(const unsigned long *dwrd, int32_t n_dwrd, int32_t iword, int32_t ibit);
 
+/* Page-locked host memory for the `out` buffer of gpusim_generate_epochs (device->host copies into
+ * it run at full PCIe rate and overlap generation).  gpusim_host_free(NULL) is a no-op. */
+void *gpusim_host_alloc(size_t n_bytes);
+void gpusim_host_free(void *p);
+
 /*
  * FLOAT_CARR_PHASE hosts only: the value of chan[i].carr_phase after n_samples executions of
  * "carr_phase += f_carr*delt; wrap into [0,1)" (gpssim.c:2245-2250) - what the removed sample loop

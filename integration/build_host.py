@@ -78,7 +78,7 @@ def build(variant: str, tmp: str) -> str:
     cmd = ["gcc", *CFLAGS, "-I", work, "-I", HERE, "-I", os.path.join(ROOT, "include"),
            os.path.join(work, "gpssim_gpu.c"), os.path.join(HERE, "gpusim_hook.c"),
            "-L", LIBDIR, "-lgpusim", "-Wl,-rpath,$ORIGIN/../../gps_sdr_sim_b200",
-           "-lm", "-o", exe]
+           "-lm", "-lpthread", "-o", exe]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -12,10 +12,16 @@
  * Environment (all optional):
  *   GPUSIM_BATCH_EPOCHS  epochs per library call            (default 256)
  *   GPUSIM_DEVICE        CUDA device ordinal                (default 0)
+ *   GPUSIM_DEVICES       number of GPUs (devices 0..n-1) to time-shard batches over (default 1):
+ *                        batch b goes to device b mod n; one worker thread per GPU generates into
+ *                        page-locked buffers, one writer thread fwrites the batches in order
+ *   GPUSIM_DEVICE_LIST   same, with explicit ordinals, e.g. "0,2,5" (or "0,0" to run two workers
+ *                        on one GPU)
  *   GPUSIM_DUMP          path: also write every table row to this file
  *                        (format below) - how tests/golden/ fixtures are made
  *   GPUSIM_DRYRUN        1: record (and dump) rows, generate nothing, write nothing
  */
+#include <pthread.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -48,6 +54,26 @@ typedef struct
 	int32_t *ibit;
 } cols_t;
 
+/* multi-GPU pipeline: a ring of batch slots; slot states advance FREE -> QUEUED -> DONE -> FREE */
+#define HOOK_MAX_DEV 16
+enum { SLOT_FREE = 0, SLOT_QUEUED = 1, SLOT_DONE = 2 };
+typedef struct
+{
+	cols_t rows;
+	unsigned char *out; /* page-locked, batch capacity */
+	int state;
+} slot_t;
+
+struct gpusim_hook;
+typedef struct
+{
+	struct gpusim_hook *h;
+	gpusim_ctx *ctx;
+	int index; /* worker d serves batches d, d+n, d+2n, ... */
+	int device;
+	pthread_t thread;
+} worker_t;
+
 struct gpusim_hook
 {
 	int N;
@@ -61,6 +87,15 @@ struct gpusim_hook
 	cols_t batch;
 	cols_t dump;
 	long epochs_done;
+	/* multi-GPU (ndev > 1) */
+	int ndev, nslots;
+	slot_t *slots;
+	worker_t workers[HOOK_MAX_DEV];
+	pthread_t writer;
+	pthread_mutex_t mu;
+	pthread_cond_t cv;
+	long seq_filled; /* batches handed to the workers so far */
+	int finishing;   /* no more batches will be queued */
 };
 
 static void die(const char *what, const char *detail)
@@ -129,6 +164,102 @@ static int sink_fwrite(void *user, const void *bytes, size_t n)
 	return fwrite(bytes, 1, n, h->fp) == n ? 0 : 1;
 }
 
+static void table_of(const cols_t *c, gpusim_epoch_table *t)
+{
+	memset(t, 0, sizeof(*t));
+	t->n_epochs = c->n;
+	t->prn = c->prn;
+	t->f_code = c->f_code;
+	t->code_phase = c->code_phase;
+	t->icode = c->icode;
+	t->nav_bits = c->nav_bits;
+	t->gain = c->gain;
+	t->carr_phasestep = c->carr_phasestep;
+	t->carr_phase = c->carr_phase;
+	t->f_carr = c->f_carr;
+	t->carr_phase_f = c->carr_phase_f;
+}
+
+/* ---- multi-GPU pipeline ------------------------------------------------------------------ */
+static void *worker_main(void *arg)
+{
+	worker_t *w = (worker_t *)arg;
+	gpusim_hook *h = w->h;
+	long seq;
+	for (seq = w->index;; seq += h->ndev)
+	{
+		slot_t *s = &h->slots[seq % h->nslots];
+		gpusim_epoch_table t;
+		int rc;
+		pthread_mutex_lock(&h->mu);
+		while (!(s->state == SLOT_QUEUED && seq < h->seq_filled) && !(h->finishing && seq >= h->seq_filled))
+			pthread_cond_wait(&h->cv, &h->mu);
+		if (seq >= h->seq_filled)
+		{
+			pthread_mutex_unlock(&h->mu);
+			return NULL;
+		}
+		pthread_mutex_unlock(&h->mu);
+
+		table_of(&s->rows, &t);
+		rc = gpusim_generate_epochs(w->ctx, &t, s->out, (size_t)h->batch.cap * gpusim_epoch_bytes(w->ctx));
+		if (rc != GPUSIM_OK)
+			die("GPU sample generation failed", gpusim_last_error(w->ctx));
+
+		pthread_mutex_lock(&h->mu);
+		s->state = SLOT_DONE;
+		pthread_cond_broadcast(&h->cv);
+		pthread_mutex_unlock(&h->mu);
+	}
+}
+
+static void *writer_main(void *arg)
+{
+	gpusim_hook *h = (gpusim_hook *)arg;
+	const size_t eb = gpusim_epoch_bytes(h->workers[0].ctx);
+	long seq;
+	for (seq = 0;; seq++)
+	{
+		slot_t *s = &h->slots[seq % h->nslots];
+		pthread_mutex_lock(&h->mu);
+		while (!(s->state == SLOT_DONE && seq < h->seq_filled) && !(h->finishing && seq >= h->seq_filled))
+			pthread_cond_wait(&h->cv, &h->mu);
+		if (seq >= h->seq_filled)
+		{
+			pthread_mutex_unlock(&h->mu);
+			return NULL;
+		}
+		pthread_mutex_unlock(&h->mu);
+
+		/* strictly in batch order: this is the reference's output file */
+		if (fwrite(s->out, 1, (size_t)s->rows.n * eb, h->fp) != (size_t)s->rows.n * eb)
+			die("Failed to write the output file", NULL);
+
+		pthread_mutex_lock(&h->mu);
+		s->state = SLOT_FREE;
+		pthread_cond_broadcast(&h->cv);
+		pthread_mutex_unlock(&h->mu);
+	}
+}
+
+/* hand the filled batch to the next GPU: swap it into a free ring slot */
+static void queue_batch(gpusim_hook *h)
+{
+	slot_t *s = &h->slots[h->seq_filled % h->nslots];
+	cols_t tmp;
+	pthread_mutex_lock(&h->mu);
+	while (s->state != SLOT_FREE)
+		pthread_cond_wait(&h->cv, &h->mu);
+	tmp = s->rows;
+	s->rows = h->batch;
+	h->batch = tmp;
+	h->batch.n = 0;
+	s->state = SLOT_QUEUED;
+	h->seq_filled++;
+	pthread_cond_broadcast(&h->cv);
+	pthread_mutex_unlock(&h->mu);
+}
+
 static void flush_batch(gpusim_hook *h)
 {
 	gpusim_epoch_table t;
@@ -137,20 +268,16 @@ static void flush_batch(gpusim_hook *h)
 	if (h->batch.n == 0)
 		return;
 
+	if (!h->dryrun && h->ndev > 1)
+	{
+		h->epochs_done += h->batch.n;
+		queue_batch(h);
+		return;
+	}
+
 	if (!h->dryrun)
 	{
-		memset(&t, 0, sizeof(t));
-		t.n_epochs = h->batch.n;
-		t.prn = h->batch.prn;
-		t.f_code = h->batch.f_code;
-		t.code_phase = h->batch.code_phase;
-		t.icode = h->batch.icode;
-		t.nav_bits = h->batch.nav_bits;
-		t.gain = h->batch.gain;
-		t.carr_phasestep = h->batch.carr_phasestep;
-		t.carr_phase = h->batch.carr_phase;
-		t.f_carr = h->batch.f_carr;
-		t.carr_phase_f = h->batch.carr_phase_f;
+		table_of(&h->batch, &t);
 
 		rc = gpusim_generate_epochs_to_sink(h->ctx, &t, sink_fwrite, h);
 		if (rc != GPUSIM_OK)
@@ -187,10 +314,31 @@ gpusim_hook *gpusim_hook_open(int iq_buff_size, double delt, int data_format, FI
 	cols_reserve(&h->batch, batch);
 	h->batch.cap = batch; /* fixed: flush when full */
 
+	h->ndev = 1;
+	if ((s = getenv("GPUSIM_DEVICE_LIST")) != NULL && *s)
+	{
+		h->ndev = 0;
+		while (*s && h->ndev < HOOK_MAX_DEV)
+		{
+			h->workers[h->ndev++].device = atoi(s);
+			while (*s && *s != ',')
+				s++;
+			if (*s == ',')
+				s++;
+		}
+	}
+	else if ((s = getenv("GPUSIM_DEVICES")) != NULL && atoi(s) > 1)
+	{
+		int d;
+		h->ndev = atoi(s) > HOOK_MAX_DEV ? HOOK_MAX_DEV : atoi(s);
+		for (d = 0; d < h->ndev; d++)
+			h->workers[d].device = d;
+	}
+
 	if (!h->dryrun)
 	{
 		gpusim_config cfg;
-		int rc;
+		int rc, d;
 		memset(&cfg, 0, sizeof(cfg));
 		cfg.abi_version = GPUSIM_ABI_VERSION;
 		cfg.device = (s = getenv("GPUSIM_DEVICE")) != NULL ? atoi(s) : 0;
@@ -199,9 +347,42 @@ gpusim_hook *gpusim_hook_open(int iq_buff_size, double delt, int data_format, FI
 		cfg.carrier_mode = h->carrier_mode;
 		cfg.max_batch_epochs = batch;
 		cfg.delt = delt;
-		rc = gpusim_create(&cfg, &h->ctx);
-		if (rc != GPUSIM_OK)
-			die("Failed to initialise the GPU sample generator", gpusim_last_error(NULL));
+		if (h->ndev == 1)
+		{
+			rc = gpusim_create(&cfg, &h->ctx);
+			if (rc != GPUSIM_OK)
+				die("Failed to initialise the GPU sample generator", gpusim_last_error(NULL));
+		}
+		else
+		{
+			/* time-sharding over GPUs: epochs are independent given their rows, no exchange needed */
+			pthread_mutex_init(&h->mu, NULL);
+			pthread_cond_init(&h->cv, NULL);
+			h->nslots = 2 * h->ndev;
+			h->slots = calloc((size_t)h->nslots, sizeof(slot_t));
+			if (h->slots == NULL)
+				die("gpusim hook out of memory", NULL);
+			for (d = 0; d < h->ndev; d++)
+			{
+				cfg.device = h->workers[d].device;
+				rc = gpusim_create(&cfg, &h->workers[d].ctx);
+				if (rc != GPUSIM_OK)
+					die("Failed to initialise the GPU sample generator", gpusim_last_error(NULL));
+				h->workers[d].h = h;
+				h->workers[d].index = d;
+			}
+			for (d = 0; d < h->nslots; d++)
+			{
+				cols_reserve(&h->slots[d].rows, batch);
+				h->slots[d].rows.cap = batch;
+				h->slots[d].out = gpusim_host_alloc((size_t)batch * gpusim_epoch_bytes(h->workers[0].ctx));
+				if (h->slots[d].out == NULL)
+					die("Failed to allocate page-locked output buffers", NULL);
+			}
+			for (d = 0; d < h->ndev; d++)
+				pthread_create(&h->workers[d].thread, NULL, worker_main, &h->workers[d]);
+			pthread_create(&h->writer, NULL, writer_main, h);
+		}
 	}
 	return h;
 }
@@ -299,6 +480,25 @@ static void write_dump(const gpusim_hook *h)
 void gpusim_hook_close(gpusim_hook *h)
 {
 	flush_batch(h);
+	if (!h->dryrun && h->ndev > 1)
+	{
+		int d;
+		pthread_mutex_lock(&h->mu);
+		h->finishing = 1;
+		pthread_cond_broadcast(&h->cv);
+		pthread_mutex_unlock(&h->mu);
+		for (d = 0; d < h->ndev; d++)
+			pthread_join(h->workers[d].thread, NULL);
+		pthread_join(h->writer, NULL);
+		for (d = 0; d < h->ndev; d++)
+			gpusim_destroy(h->workers[d].ctx);
+		for (d = 0; d < h->nslots; d++)
+		{
+			cols_free(&h->slots[d].rows);
+			gpusim_host_free(h->slots[d].out);
+		}
+		free(h->slots);
+	}
 	if (h->dump_path != NULL)
 		write_dump(h);
 	if (h->ctx != NULL)

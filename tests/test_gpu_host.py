@@ -69,3 +69,23 @@ def test_asshipped_float_host_with_gpu_binding_equals_reference_cli(name, gpu_re
     assert g.returncode == 0, g.stderr[-800:]
     assert os.path.getsize(a) == os.path.getsize(b) > 0
     assert filecmp.cmp(a, b, shallow=False)
+
+
+def test_multi_gpu_time_sharded_host_writes_the_same_file(gpu_required, tmp_path):
+    """GPUSIM_DEVICE_LIST: batches are dealt round-robin to one worker per listed device and written
+    in order by one writer.  Uses every GPU of the box (two workers on one GPU if there is only one)."""
+    import torch
+    ref = oracle_lib.ref_binary("int")
+    if ref is None or not os.path.exists(HOST):
+        pytest.skip("oracle/_ref / integration/_build were not shipped to this box")
+    n = torch.cuda.device_count()
+    devices = ",".join(str(d) for d in range(n)) if n > 1 else "0,0"
+    common = ["-e", D("brdc3540.14n"), "-u", D("circle.csv"), "-s", "2600000", "-b", "16", "-d", "25"]
+    a, b = tmp_path / "ref.bin", tmp_path / "gpu.bin"
+    r = subprocess.run([ref, *common, "-o", str(a)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-500:]
+    g = subprocess.run([HOST, *common, "-o", str(b)], capture_output=True, text=True,
+                       env=dict(os.environ, GPUSIM_BATCH_EPOCHS="24", GPUSIM_DEVICE_LIST=devices))
+    assert g.returncode == 0, g.stderr[-800:]
+    assert os.path.getsize(a) == os.path.getsize(b) > 0
+    assert filecmp.cmp(a, b, shallow=False)

@@ -436,7 +436,8 @@ GS_HD int data_sign(uint32_t nav_bits, int bitk) // +1 / -1, gpssim.c:2236
 //
 //   x      code phase of the first sample (chips)          d      per-sample addend
 //   phs    carr_phase << 7 (table index = phs >> 23)        steps  carr_phasestep << 7
-//   negw   this PRN's chips, INVERTED (bit set = chip 0 = codeCA -1), 33 words, MSB first
+//   win    chip_window(): this PRN's 32 chips from floor(x) on, INVERTED (bit set = chip 0 =
+//          codeCA -1), current chip in bit 31
 //   lut    the replicated carrier table in shared memory, lane_off this lane's replica
 //
 // The chip sign is folded into the carrier phase: negating (cos,sin) equals adding half
@@ -450,6 +451,12 @@ GS_HD typename A::tab_t lut_at(const typename A::tab_t *lut, uint32_t e, uint32_
 {
     const uint32_t off = ((e >> 16) & 0xff80u) | lane_off; // (table index << 7) | replica, bytes
     return *reinterpret_cast<const typename A::tab_t *>(reinterpret_cast<const char *>(lut) + off);
+}
+
+// the 32 (inverted) chips from chip c0 on, chip c0 in bit 31; the table continues past chip 1022
+GS_HD uint32_t chip_window(const uint32_t *negw, int c0)
+{
+    return funnel_l(negw[(c0 >> 5) + 1], negw[c0 >> 5], (uint32_t)c0 & 31u);
 }
 
 struct ChanState {
@@ -469,13 +476,12 @@ GS_HD int meta_sgain(uint32_t m) { return (int)(int32_t)m >> 16; }
 
 template <class A, int S>
 GS_HD void synth_fast(typename A::acc_t (&acc)[S], ChanState &st, const double d, const uint32_t steps,
-                      const int signed_gain, const uint32_t *negw, const typename A::tab_t *lut,
+                      const int signed_gain, const uint32_t win, const typename A::tab_t *lut,
                       const uint32_t lane_off)
 {
     double x = st.x;
     uint32_t phs = st.phs;
     const int c0 = (int)x;
-    const uint32_t win = funnel_l(negw[(c0 >> 5) + 1], negw[c0 >> 5], (uint32_t)c0 & 31u);
     const double magic = 4503599627370496.0 - (double)c0;
     const typename A::gain_t g = A::make_gain(signed_gain);
 #pragma unroll
@@ -497,13 +503,12 @@ GS_HD void synth_fast(typename A::acc_t (&acc)[S], ChanState &st, const double d
 // further; the data bit (and with it the signed gain) switches to a value prepared up front.
 template <class A, int S>
 GS_HD void synth_wrap(typename A::acc_t (&acc)[S], ChanState &st, const double d, const uint32_t steps,
-                      const int32_t gain, const uint32_t nav_bits, const uint32_t *negw,
+                      const int32_t gain, const uint32_t nav_bits, const uint32_t win,
                       const typename A::tab_t *lut, const uint32_t lane_off)
 {
     double x = st.x;
     uint32_t phs = st.phs;
     const int c0 = (int)x;
-    const uint32_t win = funnel_l(negw[(c0 >> 5) + 1], negw[c0 >> 5], (uint32_t)c0 & 31u);
     const double magic = 6755399441055744.0 - (double)c0; // 1.5 * 2^52 - c0
     const int bit_after = st.bitk + (st.icode == 19 ? 1 : 0);
     typename A::gain_t g = A::make_gain(data_sign(nav_bits, st.bitk) * gain);
@@ -574,12 +579,11 @@ GS_HD typename A::tab_t lut_at_f(const typename A::tab_t *lut, uint32_t fl, uint
 
 template <class A, int S>
 GS_HD void synth_fast_f(typename A::acc_t (&acc)[S], ChanStateF &st, const double d, const double dc,
-                        const int signed_gain, const uint32_t *negw, const typename A::tab_t *lut,
+                        const int signed_gain, const uint32_t win, const typename A::tab_t *lut,
                         const uint32_t lane_off)
 {
     double x = st.x, cph = st.cph;
     const int c0 = (int)x;
-    const uint32_t win = funnel_l(negw[(c0 >> 5) + 1], negw[c0 >> 5], (uint32_t)c0 & 31u);
     const double magic = 4503599627370496.0 - (double)c0;
     const typename A::gain_t g = A::make_gain(signed_gain);
 #pragma unroll
@@ -596,12 +600,11 @@ GS_HD void synth_fast_f(typename A::acc_t (&acc)[S], ChanStateF &st, const doubl
 
 template <class A, int S>
 GS_HD void synth_wrap_f(typename A::acc_t (&acc)[S], ChanStateF &st, const double d, const double dc,
-                        const int32_t gain, const uint32_t nav_bits, const uint32_t *negw,
+                        const int32_t gain, const uint32_t nav_bits, const uint32_t win,
                         const typename A::tab_t *lut, const uint32_t lane_off)
 {
     double x = st.x, cph = st.cph;
     const int c0 = (int)x;
-    const uint32_t win = funnel_l(negw[(c0 >> 5) + 1], negw[c0 >> 5], (uint32_t)c0 & 31u);
     const double magic = 6755399441055744.0 - (double)c0; // 1.5 * 2^52 - c0
     const int bit_after = st.bitk + (st.icode == 19 ? 1 : 0);
     typename A::gain_t g = A::make_gain(data_sign(nav_bits, st.bitk) * gain);

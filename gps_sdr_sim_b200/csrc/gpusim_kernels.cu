@@ -174,16 +174,28 @@ __device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows
         acc[j] = A::init();
 
     uint32_t sa = sm.state;
+    // The channel loop is software pipelined: the row and the code phase of channel k+1 are loaded
+    // while channel k is being generated (each channel's state slot is private to the thread, so the
+    // early loads are safe).  Without it every channel begins with a load -> convert -> load chain
+    // that only other warps could hide, and there are just four warps per scheduler.  (Prefetching
+    // more - carrier phase, chip words - measured slower: the kernel sits at the register limit.)
+    uint4 r0n = make_uint4(0, 0, 0, 0); // d, steps, cthr | prn<<16 | gain8<<24
+    double xn = 0.0;
+    if (live && nc > 0) {
+        r0n = rows4[0];
+        xn = lds_f64(sa);
+    }
     for (int k = 0; k < ncw; k++, sa += G::kStride) {
         const bool act = live && k < nc;
-        uint4 r0 = make_uint4(0, 0, 0, 0);
-        double x = 0.0;
-        bool wrap = false;
-        if (act) {
-            r0 = rows4[2 * k]; // d, steps, cthr | prn<<16 | gain8<<24
-            x = lds_f64(sa);
-            wrap = (int)x >= (int)(r0.w & cthr_mask);
+        const uint4 r0 = r0n;
+        const double x = xn;
+        if (live && k + 1 < nc) {
+            r0n = rows4[2 * k + 2];
+            xn = lds_f64(sa + G::kStride);
         }
+        bool wrap = false;
+        if (act)
+            wrap = (int)x >= (int)(r0.w & cthr_mask);
         const bool any_wrap = __any_sync(mask, wrap);
         if (act) {
             const double d = __hiloint2double((int)r0.y, (int)r0.x);
@@ -194,12 +206,12 @@ __device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows
                 const uint2 pm = lds_u32x2(sa + G::kSecond);
                 st.phs = pm.x;
                 if (!any_wrap) {
-                    synth_fast<A, SR>(acc, st, d, r0.z, meta_sgain(pm.y), nw, sm.lut, lane_off);
+                    synth_fast<A, SR>(acc, st, d, r0.z, meta_sgain(pm.y), chip_window(nw, (int)x), sm.lut, lane_off);
                 } else {
                     const uint4 r1 = rows4[2 * k + 1]; // ph0s, gain, nav_bits, icode0 | flags<<16
                     st.icode = meta_icode(pm.y);
                     st.bitk = meta_bitk(pm.y);
-                    synth_wrap<A, SR>(acc, st, d, r0.z, (int32_t)r1.y, r1.z, nw, sm.lut, lane_off);
+                    synth_wrap<A, SR>(acc, st, d, r0.z, (int32_t)r1.y, r1.z, chip_window(nw, (int)x), sm.lut, lane_off);
                     sts_u32(sa + G::kMeta, pack_meta(st.icode, st.bitk, data_sign(r1.z, st.bitk) * (int32_t)r1.y));
                 }
                 sts_f64(sa, st.x);
@@ -211,12 +223,12 @@ __device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows
                 const uint32_t meta = lds_u32(sa + G::kMeta);
                 const double dc = dcs[k];
                 if (!any_wrap) {
-                    synth_fast_f<A, SR>(acc, st, d, dc, meta_sgain(meta), nw, sm.lut, lane_off);
+                    synth_fast_f<A, SR>(acc, st, d, dc, meta_sgain(meta), chip_window(nw, (int)x), sm.lut, lane_off);
                 } else {
                     const uint4 r1 = rows4[2 * k + 1];
                     st.icode = meta_icode(meta);
                     st.bitk = meta_bitk(meta);
-                    synth_wrap_f<A, SR>(acc, st, d, dc, (int32_t)r1.y, r1.z, nw, sm.lut, lane_off);
+                    synth_wrap_f<A, SR>(acc, st, d, dc, (int32_t)r1.y, r1.z, chip_window(nw, (int)x), sm.lut, lane_off);
                     sts_u32(sa + G::kMeta, pack_meta(st.icode, st.bitk, data_sign(r1.z, st.bitk) * (int32_t)r1.y));
                 }
                 sts_f64(sa, st.x);

@@ -58,11 +58,11 @@ void emu_run(const Tables &T, const DevRow *rows, int nc, ChanState *st, uint32_
         const bool wrap = (int)st[k].x >= (int)r.cthr || force_wrap;
         const uint32_t *nw = T.negw.data() + (size_t)r.prn * kCaWords;
         if (!wrap) {
-            synth_fast<A, SR>(acc, st[k], r.d, (uint32_t)r.steps, meta_sgain(meta[k]), nw, lut, lane_off);
+            synth_fast<A, SR>(acc, st[k], r.d, (uint32_t)r.steps, meta_sgain(meta[k]), chip_window(nw, (int)st[k].x), lut, lane_off);
         } else {
             st[k].icode = meta_icode(meta[k]);
             st[k].bitk = meta_bitk(meta[k]);
-            synth_wrap<A, SR>(acc, st[k], r.d, (uint32_t)r.steps, r.gain, r.nav_bits, nw, lut, lane_off);
+            synth_wrap<A, SR>(acc, st[k], r.d, (uint32_t)r.steps, r.gain, r.nav_bits, chip_window(nw, (int)st[k].x), lut, lane_off);
             meta[k] = pack_meta(st[k].icode, st[k].bitk, data_sign(r.nav_bits, st[k].bitk) * r.gain);
         }
     }
@@ -108,11 +108,11 @@ void emu_run_f(const Tables &T, const DevRow *rows, const double *dcs, int nc, C
         const bool wrap = (int)st[k].x >= (int)r.cthr || force_wrap;
         const uint32_t *nw = T.negw.data() + (size_t)r.prn * kCaWords;
         if (!wrap) {
-            synth_fast_f<A, SR>(acc, st[k], r.d, dcs[k], meta_sgain(meta[k]), nw, lut, lane_off);
+            synth_fast_f<A, SR>(acc, st[k], r.d, dcs[k], meta_sgain(meta[k]), chip_window(nw, (int)st[k].x), lut, lane_off);
         } else {
             st[k].icode = meta_icode(meta[k]);
             st[k].bitk = meta_bitk(meta[k]);
-            synth_wrap_f<A, SR>(acc, st[k], r.d, dcs[k], r.gain, r.nav_bits, nw, lut, lane_off);
+            synth_wrap_f<A, SR>(acc, st[k], r.d, dcs[k], r.gain, r.nav_bits, chip_window(nw, (int)st[k].x), lut, lane_off);
             meta[k] = pack_meta(st[k].icode, st[k].bitk, data_sign(r.nav_bits, st[k].bitk) * r.gain);
         }
     }

@@ -561,6 +561,22 @@ GS_HD double carrier_step(double cph, const double dc) // gpssim.c:2245-2250, sc
         cph = dadd(cph, kCarrMod);
     return cph;
 }
+// The same update when the sign of dc is known: from [0,512) a rising phase can only leave at the
+// top, a falling one only at the bottom, so one of the two tests of the reference can never fire.
+// One add, one compare, one predicated add - no branch.
+template <bool kFalling>
+GS_HD double carrier_step_signed(double cph, const double dc)
+{
+    cph = dadd(cph, dc);
+    if (kFalling) {
+        if (cph < 0.0)
+            cph = dadd(cph, kCarrMod);
+    } else {
+        if (cph >= kCarrMod)
+            cph = dadd(cph, -kCarrMod);
+    }
+    return cph;
+}
 
 struct ChanStateF {
     double x;      // code phase
@@ -577,7 +593,7 @@ GS_HD typename A::tab_t lut_at_f(const typename A::tab_t *lut, uint32_t fl, uint
     return *reinterpret_cast<const typename A::tab_t *>(reinterpret_cast<const char *>(lut) + off);
 }
 
-template <class A, int S>
+template <class A, int S, bool kFalling>
 GS_HD void synth_fast_f(typename A::acc_t (&acc)[S], ChanStateF &st, const double d, const double dc,
                         const int signed_gain, const uint32_t win, const typename A::tab_t *lut,
                         const uint32_t lane_off)
@@ -592,13 +608,13 @@ GS_HD void synth_fast_f(typename A::acc_t (&acc)[S], ChanStateF &st, const doubl
         // (win << adv) has the current (inverted) chip in bit 31; >>16 puts it on offset bit 15
         A::mad(acc[j], lut_at_f<A>(lut, carrier_offset_bits(cph), (win << adv) & 0x80000000u, lane_off), g);
         x = dadd(x, d);
-        cph = carrier_step(cph, dc);
+        cph = carrier_step_signed<kFalling>(cph, dc);
     }
     st.x = x;
     st.cph = cph;
 }
 
-template <class A, int S>
+template <class A, int S, bool kFalling>
 GS_HD void synth_wrap_f(typename A::acc_t (&acc)[S], ChanStateF &st, const double d, const double dc,
                         const int32_t gain, const uint32_t nav_bits, const uint32_t win,
                         const typename A::tab_t *lut, const uint32_t lane_off)
@@ -615,7 +631,7 @@ GS_HD void synth_wrap_f(typename A::acc_t (&acc)[S], ChanStateF &st, const doubl
         const uint32_t adv = chips_since_signed(x, magic) + wrap_off;
         A::mad(acc[j], lut_at_f<A>(lut, carrier_offset_bits(cph), (win << adv) & 0x80000000u, lane_off), g);
         x = dadd(x, d);
-        cph = carrier_step(cph, dc);
+        cph = carrier_step_signed<kFalling>(cph, dc);
         const bool wrapped = x >= (double)kCaLen;
         x = wrapped ? dadd(x, -(double)kCaLen) : x;
         wrap_off = wrapped ? (uint32_t)kCaLen : wrap_off;

@@ -222,13 +222,20 @@ __device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows
                 st.cph = lds_f64(sa + G::kSecond);
                 const uint32_t meta = lds_u32(sa + G::kMeta);
                 const double dc = dcs[k];
+                // rising and falling carrier phase have their own loops (one wrap test each)
                 if (!any_wrap) {
-                    synth_fast_f<A, SR>(acc, st, d, dc, meta_sgain(meta), chip_window(nw, (int)x), sm.lut, lane_off);
+                    if (dc < 0.0)
+                        synth_fast_f<A, SR, true>(acc, st, d, dc, meta_sgain(meta), chip_window(nw, (int)x), sm.lut, lane_off);
+                    else
+                        synth_fast_f<A, SR, false>(acc, st, d, dc, meta_sgain(meta), chip_window(nw, (int)x), sm.lut, lane_off);
                 } else {
                     const uint4 r1 = rows4[2 * k + 1];
                     st.icode = meta_icode(meta);
                     st.bitk = meta_bitk(meta);
-                    synth_wrap_f<A, SR>(acc, st, d, dc, (int32_t)r1.y, r1.z, chip_window(nw, (int)x), sm.lut, lane_off);
+                    if (dc < 0.0)
+                        synth_wrap_f<A, SR, true>(acc, st, d, dc, (int32_t)r1.y, r1.z, chip_window(nw, (int)x), sm.lut, lane_off);
+                    else
+                        synth_wrap_f<A, SR, false>(acc, st, d, dc, (int32_t)r1.y, r1.z, chip_window(nw, (int)x), sm.lut, lane_off);
                     sts_u32(sa + G::kMeta, pack_meta(st.icode, st.bitk, data_sign(r1.z, st.bitk) * (int32_t)r1.y));
                 }
                 sts_f64(sa, st.x);

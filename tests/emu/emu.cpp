@@ -108,11 +108,17 @@ void emu_run_f(const Tables &T, const DevRow *rows, const double *dcs, int nc, C
         const bool wrap = (int)st[k].x >= (int)r.cthr || force_wrap;
         const uint32_t *nw = T.negw.data() + (size_t)r.prn * kCaWords;
         if (!wrap) {
-            synth_fast_f<A, SR>(acc, st[k], r.d, dcs[k], meta_sgain(meta[k]), chip_window(nw, (int)st[k].x), lut, lane_off);
+            if (dcs[k] < 0.0)
+                synth_fast_f<A, SR, true>(acc, st[k], r.d, dcs[k], meta_sgain(meta[k]), chip_window(nw, (int)st[k].x), lut, lane_off);
+            else
+                synth_fast_f<A, SR, false>(acc, st[k], r.d, dcs[k], meta_sgain(meta[k]), chip_window(nw, (int)st[k].x), lut, lane_off);
         } else {
             st[k].icode = meta_icode(meta[k]);
             st[k].bitk = meta_bitk(meta[k]);
-            synth_wrap_f<A, SR>(acc, st[k], r.d, dcs[k], r.gain, r.nav_bits, chip_window(nw, (int)st[k].x), lut, lane_off);
+            if (dcs[k] < 0.0)
+                synth_wrap_f<A, SR, true>(acc, st[k], r.d, dcs[k], r.gain, r.nav_bits, chip_window(nw, (int)st[k].x), lut, lane_off);
+            else
+                synth_wrap_f<A, SR, false>(acc, st[k], r.d, dcs[k], r.gain, r.nav_bits, chip_window(nw, (int)st[k].x), lut, lane_off);
             meta[k] = pack_meta(st[k].icode, st[k].bitk, data_sign(r.nav_bits, st[k].bitk) * r.gain);
         }
     }

@@ -20,6 +20,7 @@ CASES = {
     "config1_static_b16": ["-l", "30.286502,120.032669,100", "-d", "30", "-s", "2600000", "-b", "16"],
     "config2_circle_b8": ["-u", "circle.csv", "-s", "2600000", "-b", "8", "-d", "40"],
     "config3_satellite_b16": ["-u", "satellite.csv", "-i", "-s", "2600000", "-b", "16", "-d", "35"],
+    "config3_rocket_b16": ["-u", "rocket.csv", "-i", "-s", "2600000", "-b", "16", "-d", "35"],
     "config4_nmea_b1": ["-g", "triumphv3.txt", "-s", "1000000", "-b", "1"],
     "config5_prefix_20msps": ["-l", "30.286502,120.032669,100", "-d", "2", "-s", "20000000", "-b", "16"],
     "odd_rate_generic": ["-l", "30.286502,120.032669,100", "-d", "3", "-s", "1234570", "-b", "8"],

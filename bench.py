@@ -190,6 +190,24 @@ def ncu_traffic():
         return None
 
 
+def bind_to_gpu_cpus(index: int):
+    """Pin this rank to the CPUs closest to its GPU (NVML's affinity mask) so that the page-locked
+    output buffer is allocated on the NUMA node the GPU's PCIe link hangs off.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus ({cpus[0]}..{cpus[-1]})"
+    except Exception as exc:  # noqa: BLE001
+        return f"unbound ({type(exc).__name__})"
+    return "unbound"
+
+
 def main_b200(args):
     import torch
     import torch.distributed as dist
@@ -202,6 +220,7 @@ def main_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - this path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_cpus(local_rank)    # before any pinned allocation: keep staging memory NUMA-local
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -295,6 +314,7 @@ def main_b200(args):
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": out_bytes, "ms_per_step": e2e_ms / args.steps,
                     "x_realtime": e2e_value / (10.0 * N_SAMPLES), "api": "gpusim_generate_epochs (C ABI), pinned host output",
+                    "rank0_cpu_binding": numa,
                     "host_checksum": checksum},
             "gpu_launches": launches_per_step * args.steps,
             "kernels": {"k1_chain_ms": sum(k1_ms) / len(k1_ms), "k2_synth_ms": k2, "tuned_kernel": bool(fast_path)},

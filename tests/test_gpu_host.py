@@ -90,3 +90,18 @@ def test_multi_gpu_time_sharded_host_writes_the_same_file(gpu_required, tmp_path
     assert g.returncode == 0, g.stderr[-800:]
     assert os.path.getsize(a) == os.path.getsize(b) > 0
     assert filecmp.cmp(a, b, shallow=False)
+
+
+def test_stdout_streaming_keeps_the_format_contract(gpu_required, tmp_path):
+    """`-o -` (gpssim.c:2103-2111): the samples go to stdout in epoch order, e.g. into a player's pipe.
+    The ordered sink writes exactly the file bytes (output sink)."""
+    ref = oracle_lib.ref_binary("int")
+    if ref is None or not os.path.exists(HOST):
+        pytest.skip("oracle/_ref / integration/_build were not shipped to this box")
+    common = ["-e", D("brdc3540.14n"), "-u", D("circle.csv"), "-s", "2600000", "-b", "8", "-d", "12"]
+    a = tmp_path / "ref.bin"
+    r = subprocess.run([ref, *common, "-o", str(a)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-500:]
+    g = subprocess.run([HOST, *common, "-o", "-"], capture_output=True, env=dict(os.environ, GPUSIM_BATCH_EPOCHS="40"))
+    assert g.returncode == 0, g.stderr[-800:]
+    assert g.stdout == a.read_bytes()

@@ -81,3 +81,37 @@ def test_carrier_chain_equals_sequential_replay(x0, f_carr, delt, n):
     _, end_o = oracle_lib.carrier_phase_checkpoints(x0, f_carr, delt, n, n)
     _, _, end_j = emu_lib.phase_chain(512.0 * x0, 512.0 * d, 512.0, n, 1 << 30)
     assert np.float64(end_o * 512.0).view(np.uint64) == np.float64(end_j).view(np.uint64)
+
+
+def test_chain_walk_property_random_steps_and_moduli():
+    """Property (hypothesis): for random start, step (either sign, 2^-8 .. 2 chips per sample) and sample
+    count, the jump walk equals the plain sequential recurrence bit for bit - checkpoints and final value."""
+    from hypothesis import given, settings, strategies as st
+
+    def replay(x, d, mod, n, every):
+        out = []
+        for i in range(n + 1):
+            if i % every == 0:
+                out.append(x)
+            if i == n:
+                break
+            x = np.float64(x) + np.float64(d)
+            if x >= mod:
+                x = x - np.float64(mod)
+            elif x < 0.0:
+                x = x + np.float64(mod)
+        return np.array(out, dtype=np.float64), float(x)
+
+    @settings(max_examples=250, deadline=None)
+    @given(frac=st.floats(0.0, 1.0, exclude_max=True), mant=st.floats(1.0, 2.0, exclude_max=True),
+           expo=st.integers(-8, 0), neg=st.booleans(), mod=st.sampled_from([1023.0, 512.0]),
+           n=st.integers(1, 6000), every=st.sampled_from([8, 200, 520, 4096]))
+    def check(frac, mant, expo, neg, mod, n, every):
+        d = float(np.ldexp(mant, expo)) * (-1.0 if neg else 1.0)
+        x0 = float(np.float64(frac) * np.float64(mod))
+        want, end_w = replay(x0, d, mod, n, every)
+        got, _, end_g = emu_lib.phase_chain(x0, d, mod, n, every)
+        assert np.array_equal(want.view(np.uint64), got[:want.size].view(np.uint64))
+        assert np.float64(end_w).view(np.uint64) == np.float64(end_g).view(np.uint64)
+
+    check()

@@ -148,7 +148,7 @@ SynthKernel plan_job(gpusim_ctx *ctx, int first, int n, uint8_t *out_dev, Device
     job.n_samples = ctx->cfg.samples_per_epoch;
 
     SynthKernel which = SynthKernel::Tuned32;
-    if (ctx->opt_force_generic || ctx->needs_generic || (job.n_samples % 32) != 0 || ctx->d_max >= 2.0)
+    if (ctx->opt_force_generic || ctx->needs_generic || (job.n_samples % 8) != 0 || ctx->d_max >= 2.0)
         which = SynthKernel::Generic;
     else if (ctx->d_max > 0.9999)
         which = SynthKernel::Tuned16;

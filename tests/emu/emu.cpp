@@ -209,8 +209,8 @@ int emu_generate(const gpusim_epoch_table *t, int N, double delt, int fmt, int c
     static const Tables T;
     const size_t eb = fmt == 1 ? (size_t)(N / 4) : fmt == 8 ? (size_t)2 * N : (size_t)4 * N;
     const int kc = (N + chunk - 1) / chunk;
-    // tuned kernels: chunks of a multiple of 8 samples (aligned layout) inside epochs of a multiple of 32
-    if ((kernel == 2 ? chunk % 32 != 0 : chunk % 8 != 0) || (kernel != 2 && N % 32 != 0))
+    // tuned kernels: chunks and epochs of a multiple of 8 samples (runs of 32/16 plus 8-sample tails)
+    if ((kernel == 2 ? chunk % 32 != 0 : chunk % 8 != 0) || (kernel != 2 && N % 8 != 0))
         return -1;
     std::vector<double> ckx((size_t)kMaxChan * kc);
     std::vector<uint16_t> ckw((size_t)kMaxChan * kc);

@@ -60,6 +60,11 @@ SCENARIOS = {
     # a sample rate whose epoch length is not a multiple of 32 (generic kernel), 20 MS/s short run
     "odd_rate_int_b16": ("int", STATIC + ["-d", "0.5", "-s", "1234570", "-b", "16"], None),
     "odd_rate_int_b1": ("int", STATIC + ["-d", "0.5", "-s", "1234570", "-b", "1"], None),
+    # 2.5 MS/s: epochs of 250 000 samples - a multiple of 8 but not of 32, and a code period (2500
+    # samples) that cannot be cut into chunks of a multiple of 8: tuned kernel, plain layout, 8-sample tails
+    "rate2500k_int_b16": ("int", STATIC + ["-d", "0.4", "-s", "2500000", "-b", "16"], None),
+    "rate2500k_int_b1": ("int", STATIC + ["-d", "0.4", "-s", "2500000", "-b", "1"], None),
+    "rate2500k_float_b8": ("float", STATIC + ["-d", "0.4", "-s", "2500000", "-b", "8"], None),
     "static_int_20msps_b16": ("int", STATIC + ["-d", "0.3", "-s", "20000000", "-b", "16"], None),
 }
 

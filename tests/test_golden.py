@@ -36,7 +36,7 @@ def test_oracle_reproduces_reference_bytes(name):
 
 def _kernel_for(table):
     d_max = float((table.f_code * table.delt).max())
-    if table.samples_per_epoch % 32 != 0:
+    if table.samples_per_epoch % 8 != 0:
         return emu_lib.GENERIC
     return emu_lib.TUNED32 if d_max <= 0.9999 else emu_lib.TUNED16
 

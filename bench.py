@@ -235,9 +235,11 @@ def main_b200(args):
     out_bytes = count * eb
 
     sim = gs.GpuSim(N_SAMPLES, table.delt, FMT, gs.CARRIER_INT, max_batch_epochs=count, device=local_rank)
+    if args.no_pipeline:
+        sim.set_option("pipeline", 0)
     sim.upload_table(table)                      # tables resident in HBM before the timed region
     out = torch.empty(out_bytes, dtype=torch.uint8, device="cuda")
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()                 # a real stream: calls are asynchronous and pipeline
 
     def step():
         sim.generate_device(0, count, out.data_ptr(), out.numel(), stream=stream.cuda_stream)
@@ -317,7 +319,8 @@ def main_b200(args):
                     "rank0_cpu_binding": numa,
                     "host_checksum": checksum},
             "gpu_launches": launches_per_step * args.steps,
-            "kernels": {"k1_chain_ms": sum(k1_ms) / len(k1_ms), "k2_synth_ms": k2, "tuned_kernel": bool(fast_path)},
+            "kernels": {"k1_chain_ms": sum(k1_ms) / len(k1_ms), "k2_synth_ms": k2, "tuned_kernel": bool(fast_path),
+                        "chain_overlaps_previous_synth": not args.no_pipeline},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "peak_source": peak_src,
                          "kernel": "k2_synth<8,32>", "algorithmic_bytes_per_launch": out_bytes,
@@ -340,6 +343,7 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-pipeline", action="store_true", help="A/B: chain kernel on the caller's stream, no overlap between steps")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3          # timing rule: at least three untimed passes

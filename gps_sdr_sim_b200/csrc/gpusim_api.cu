@@ -23,7 +23,8 @@ namespace {
 thread_local std::string g_create_error;
 
 constexpr size_t kStageBytes = 64u << 20;      // one pinned staging buffer / sub-batch of output
-constexpr size_t kCheckpointBudget = 1u << 30; // device bytes for K1 checkpoints
+constexpr int kOverlapMinSamples = 208000; // samples per epoch from which K1 is overlapped with the previous K2
+constexpr size_t kCheckpointBudget = 1u << 29; // device bytes for ONE set of K1 checkpoints (there are two)
 
 } // namespace
 
@@ -32,8 +33,14 @@ struct gpusim_ctx {
     size_t epoch_bytes = 0;
     std::string err;
 
-    cudaStream_t s_compute = nullptr, s_copy = nullptr;
-    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_t2 = nullptr;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr, s_chain = nullptr;
+    // Two checkpoint sets ("slots") alternate between consecutive generate calls, so that the chain
+    // kernel of call i+1 (on s_chain) can run while the synthesis kernel of call i is still busy.
+    // Per slot: chain start/end, synthesis start/end (the last one also guards the slot's reuse).
+    cudaEvent_t ev_c0[2] = {nullptr, nullptr}, ev_c1[2] = {nullptr, nullptr};
+    cudaEvent_t ev_s0[2] = {nullptr, nullptr}, ev_s1[2] = {nullptr, nullptr};
+    unsigned seq = 0;
+    int last_slot = 0;
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
 
     // constant tables
@@ -51,11 +58,11 @@ struct gpusim_ctx {
     double d_max = 0.0;
 
     // checkpoints, sized for min_chunk
-    double *d_ck_x = nullptr;
-    uint16_t *d_ck_w = nullptr;
+    double *d_ck_x[2] = {nullptr, nullptr};
+    uint16_t *d_ck_w[2] = {nullptr, nullptr};
     unsigned int *d_work = nullptr;
     // FLOAT_CARR_PHASE hosts: 512*RN(f_carr*delt), 512*carr_phase at epoch start, carrier checkpoints
-    double *d_dc = nullptr, *h_dc = nullptr, *d_cph0 = nullptr, *h_cph0 = nullptr, *d_ck_c = nullptr;
+    double *d_dc = nullptr, *h_dc = nullptr, *d_cph0 = nullptr, *h_cph0 = nullptr, *d_ck_c[2] = {nullptr, nullptr};
     int sm_count = 148;
     int min_chunk = 128;
 
@@ -64,7 +71,7 @@ struct gpusim_ctx {
     uint8_t *h_stage[2] = {nullptr, nullptr};
 
     // options
-    int opt_chunk = 0, opt_force_generic = 0, opt_force_slow = 0, opt_chain_replay = 0, opt_accum = 1, opt_layout = 0;
+    int opt_chunk = 0, opt_force_generic = 0, opt_force_slow = 0, opt_chain_replay = 0, opt_accum = 1, opt_layout = 0, opt_pipeline = 1;
 
     gpusim_timing timing{};
 };
@@ -123,18 +130,18 @@ int ensure_stage(gpusim_ctx *ctx)
 }
 
 // describe the work for uploaded epochs [first, first+n): layout, chunking, kernel choice
-SynthKernel plan_job(gpusim_ctx *ctx, int first, int n, uint8_t *out_dev, DeviceJob &job)
+SynthKernel plan_job(gpusim_ctx *ctx, int first, int n, uint8_t *out_dev, DeviceJob &job, int slot)
 {
     job = DeviceJob{};
     job.rows = ctx->d_rows + (size_t)first * kMaxChan;
     job.nch = ctx->d_nch + first;
     job.x0 = ctx->d_x0 + (size_t)first * kMaxChan;
-    job.ck_x = ctx->d_ck_x;
-    job.ck_w = ctx->d_ck_w;
+    job.ck_x = ctx->d_ck_x[slot];
+    job.ck_w = ctx->d_ck_w[slot];
     job.carrier_float = ctx->cfg.carrier_mode == GPUSIM_CARRIER_FLOAT ? 1 : 0;
     job.dc = ctx->d_dc ? ctx->d_dc + (size_t)first * kMaxChan : nullptr;
     job.cph0 = ctx->d_cph0 ? ctx->d_cph0 + (size_t)first * kMaxChan : nullptr;
-    job.ck_c = ctx->d_ck_c;
+    job.ck_c = ctx->d_ck_c[slot];
     job.lut_wide = ctx->d_lut;
     job.lut_f32 = ctx->d_lut_f32;
     job.accum = ctx->opt_accum;
@@ -142,7 +149,8 @@ SynthKernel plan_job(gpusim_ctx *ctx, int first, int n, uint8_t *out_dev, Device
     job.cos16 = ctx->d_cos16;
     job.negw = ctx->d_negw;
     job.out = out_dev;
-    job.work_counter = ctx->d_work;
+    job.work_counter = ctx->d_work + 8 * slot;
+    job.shared_sm = 0;
     job.sm_count = ctx->sm_count;
     job.n_epochs = n;
     job.n_samples = ctx->cfg.samples_per_epoch;
@@ -214,21 +222,38 @@ DeviceJob sub_job(const gpusim_ctx *ctx, const DeviceJob &whole, int first, int 
     return job;
 }
 
-// launch K1 + K2 for uploaded epochs [first, first+n) into out_dev on `stream`
-int launch_range(gpusim_ctx *ctx, int first, int n, uint8_t *out_dev, cudaStream_t stream, bool timed)
+// Launch K1 + K2 for uploaded epochs [first, first+n) into out_dev.  K2 runs on `stream`; K1 runs on
+// the library's chain stream as soon as the checkpoint slot is free, i.e. concurrently with the K2 of
+// the PREVIOUS call when calls are issued back to back (a stream of batches).  K1 is a latency-bound
+// kernel of a few warps per SM; K2 is built to leave it the registers it needs.
+int launch_range(gpusim_ctx *ctx, int first, int n, uint8_t *out_dev, cudaStream_t stream)
 {
     if (n <= 0)
         return GPUSIM_OK;
+    const int slot = (int)(ctx->seq++ & 1u);
     DeviceJob job;
-    const SynthKernel which = plan_job(ctx, first, n, out_dev, job);
-    if (timed)
-        GS_CUDA(ctx, cudaEventRecord(ctx->ev_t0, stream));
-    GS_CUDA(ctx, launch_chain(job, ctx->opt_chain_replay ? ChainAlgo::Replay : ChainAlgo::Jump, stream));
-    if (timed)
-        GS_CUDA(ctx, cudaEventRecord(ctx->ev_t1, stream));
+    const SynthKernel which = plan_job(ctx, first, n, out_dev, job, slot);
+    // Overlap pays when the synthesis kernel outlasts a chain kernel that is squeezed into the
+    // registers K2 leaves free (there it runs ~4x slower than alone, and both scale with epochs x
+    // channels, so the criterion is the epoch length): measured break-even near 200 000 samples per
+    // epoch.  FLOAT and the rarely used kernels have no shared-SM build - same stream for them.
+    // And only when there is something to overlap with: the previous call's K2 is still in flight.
+    bool overlap = ctx->opt_pipeline != 0 && !job.carrier_float && which == SynthKernel::Tuned32 && job.accum == 1;
+    if (overlap && ctx->opt_pipeline != 2) {
+        overlap = job.n_samples >= kOverlapMinSamples && cudaEventQuery(ctx->ev_s1[slot ^ 1]) == cudaErrorNotReady;
+        (void)cudaGetLastError(); // "not ready" is an answer, not an error
+    }
+    job.shared_sm = overlap ? 1 : 0;
+    cudaStream_t cs = overlap ? ctx->s_chain : stream;
+    GS_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_s1[slot], 0)); // K2 of two calls ago read this slot
+    GS_CUDA(ctx, cudaEventRecord(ctx->ev_c0[slot], cs));
+    GS_CUDA(ctx, launch_chain(job, ctx->opt_chain_replay ? ChainAlgo::Replay : ChainAlgo::Jump, cs));
+    GS_CUDA(ctx, cudaEventRecord(ctx->ev_c1[slot], cs));
+    GS_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_c1[slot], 0));
+    GS_CUDA(ctx, cudaEventRecord(ctx->ev_s0[slot], stream));
     GS_CUDA(ctx, launch_synth(job, which, stream));
-    if (timed)
-        GS_CUDA(ctx, cudaEventRecord(ctx->ev_t2, stream));
+    GS_CUDA(ctx, cudaEventRecord(ctx->ev_s1[slot], stream));
+    ctx->last_slot = slot;
     ctx->timing.launches += 2;
     ctx->timing.fast_path = (which != SynthKernel::Generic) ? 1 : 0;
     return GPUSIM_OK;
@@ -237,12 +262,23 @@ int launch_range(gpusim_ctx *ctx, int first, int n, uint8_t *out_dev, cudaStream
 int collect_timing(gpusim_ctx *ctx)
 {
     float a = 0.f, b = 0.f;
-    GS_CUDA(ctx, cudaEventSynchronize(ctx->ev_t2));
-    GS_CUDA(ctx, cudaEventElapsedTime(&a, ctx->ev_t0, ctx->ev_t1));
-    GS_CUDA(ctx, cudaEventElapsedTime(&b, ctx->ev_t1, ctx->ev_t2));
+    const int slot = ctx->last_slot;
+    GS_CUDA(ctx, cudaEventSynchronize(ctx->ev_s1[slot]));
+    GS_CUDA(ctx, cudaEventElapsedTime(&a, ctx->ev_c0[slot], ctx->ev_c1[slot]));
+    GS_CUDA(ctx, cudaEventElapsedTime(&b, ctx->ev_s0[slot], ctx->ev_s1[slot]));
     ctx->timing.chain_ms += a;
     ctx->timing.synth_ms += b;
     ctx->timing.total_ms += a + b;
+    return GPUSIM_OK;
+}
+
+// no kernel of an earlier call may still be reading the uploaded rows or a checkpoint slot
+int drain(gpusim_ctx *ctx)
+{
+    GS_CUDA(ctx, cudaStreamSynchronize(ctx->s_chain));
+    GS_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
+    for (int i = 0; i < 2; i++)
+        GS_CUDA(ctx, cudaEventSynchronize(ctx->ev_s1[i]));
     return GPUSIM_OK;
 }
 
@@ -288,18 +324,24 @@ void gpusim_destroy(gpusim_ctx *ctx)
     if (!ctx)
         return;
     cudaSetDevice(ctx->cfg.device);
+    if (ctx->s_chain) cudaStreamSynchronize(ctx->s_chain);
     if (ctx->s_compute) cudaStreamSynchronize(ctx->s_compute);
     if (ctx->s_copy) cudaStreamSynchronize(ctx->s_copy);
     cudaFree(ctx->d_lut); cudaFree(ctx->d_lut_f32); cudaFree(ctx->d_sin16); cudaFree(ctx->d_cos16); cudaFree(ctx->d_negw);
     cudaFree(ctx->d_rows); cudaFree(ctx->d_nch); cudaFree(ctx->d_x0);
-    cudaFree(ctx->d_ck_x); cudaFree(ctx->d_ck_w); cudaFree(ctx->d_work); cudaFree(ctx->d_out);
-    cudaFree(ctx->d_dc); cudaFree(ctx->d_cph0); cudaFree(ctx->d_ck_c);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(ctx->d_ck_x[i]); cudaFree(ctx->d_ck_w[i]); cudaFree(ctx->d_ck_c[i]);
+    }
+    cudaFree(ctx->d_work); cudaFree(ctx->d_out);
+    cudaFree(ctx->d_dc); cudaFree(ctx->d_cph0);
     cudaFreeHost(ctx->h_dc); cudaFreeHost(ctx->h_cph0);
     cudaFreeHost(ctx->h_rows); cudaFreeHost(ctx->h_nch); cudaFreeHost(ctx->h_x0);
     cudaFreeHost(ctx->h_stage[0]); cudaFreeHost(ctx->h_stage[1]);
-    for (cudaEvent_t ev : {ctx->ev_t0, ctx->ev_t1, ctx->ev_t2, ctx->ev_done[0], ctx->ev_done[1],
+    for (cudaEvent_t ev : {ctx->ev_c0[0], ctx->ev_c0[1], ctx->ev_c1[0], ctx->ev_c1[1], ctx->ev_s0[0], ctx->ev_s0[1],
+                           ctx->ev_s1[0], ctx->ev_s1[1], ctx->ev_done[0], ctx->ev_done[1],
                            ctx->ev_copied[0], ctx->ev_copied[1]})
         if (ev) cudaEventDestroy(ev);
+    if (ctx->s_chain) cudaStreamDestroy(ctx->s_chain);
     if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
     delete ctx;
@@ -344,10 +386,14 @@ int gpusim_create(const gpusim_config *cfg, gpusim_ctx **out_ctx)
 
     GS_CREATE(cudaSetDevice(cfg->device));
     GS_CREATE(cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));
+    GS_CREATE(cudaStreamCreateWithFlags(&ctx->s_chain, cudaStreamNonBlocking));
     GS_CREATE(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
-    GS_CREATE(cudaEventCreate(&ctx->ev_t0));
-    GS_CREATE(cudaEventCreate(&ctx->ev_t1));
-    GS_CREATE(cudaEventCreate(&ctx->ev_t2));
+    for (int i = 0; i < 2; i++) {
+        GS_CREATE(cudaEventCreate(&ctx->ev_c0[i]));
+        GS_CREATE(cudaEventCreate(&ctx->ev_c1[i]));
+        GS_CREATE(cudaEventCreate(&ctx->ev_s0[i]));
+        GS_CREATE(cudaEventCreate(&ctx->ev_s1[i]));
+    }
     for (int i = 0; i < 2; i++) {
         GS_CREATE(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
         GS_CREATE(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
@@ -399,11 +445,14 @@ int gpusim_create(const gpusim_config *cfg, gpusim_ctx **out_ctx)
     while (rows * (size_t)kc_for(N, ctx->min_chunk) * (cf ? 18 : 10) > kCheckpointBudget && ctx->min_chunk < (1 << 20))
         ctx->min_chunk *= 2;
     const size_t cks = rows * (size_t)kc_for(N, ctx->min_chunk);
-    GS_CREATE(cudaMalloc(&ctx->d_ck_x, cks * sizeof(double)));
-    GS_CREATE(cudaMalloc(&ctx->d_ck_w, cks * sizeof(uint16_t)));
+    for (int i = 0; i < 2; i++) {
+        GS_CREATE(cudaMalloc(&ctx->d_ck_x[i], cks * sizeof(double)));
+        GS_CREATE(cudaMalloc(&ctx->d_ck_w[i], cks * sizeof(uint16_t)));
+        if (cf)
+            GS_CREATE(cudaMalloc(&ctx->d_ck_c[i], cks * sizeof(double)));
+    }
     GS_CREATE(cudaMalloc(&ctx->d_work, 64));
     if (cf) {
-        GS_CREATE(cudaMalloc(&ctx->d_ck_c, cks * sizeof(double)));
         GS_CREATE(cudaMalloc(&ctx->d_dc, rows * sizeof(double)));
         GS_CREATE(cudaMalloc(&ctx->d_cph0, rows * sizeof(double)));
         GS_CREATE(cudaMallocHost(&ctx->h_dc, rows * sizeof(double)));
@@ -427,6 +476,7 @@ int gpusim_set_option(gpusim_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "chain_replay")) ctx->opt_chain_replay = (int)value;
     else if (!strcmp(key, "accum")) ctx->opt_accum = (int)value;
     else if (!strcmp(key, "layout")) ctx->opt_layout = (int)value;
+    else if (!strcmp(key, "pipeline")) ctx->opt_pipeline = (int)value;
     else return fail(ctx, GPUSIM_ERR_ARG, "unknown option '%s'", key);
     return GPUSIM_OK;
 }
@@ -446,7 +496,11 @@ int gpusim_upload_table(gpusim_ctx *ctx, const gpusim_epoch_table *t)
         return fail(ctx, GPUSIM_ERR_ARG, "FLOAT_CARR_PHASE tables need f_carr and carr_phase_f");
     GS_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     // the previous upload may still be read by kernels in flight
-    GS_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
+    {
+        int rc_drain = drain(ctx);
+        if (rc_drain != GPUSIM_OK)
+            return rc_drain;
+    }
 
     const double delt = ctx->cfg.delt;
     ctx->needs_generic = false;
@@ -531,7 +585,7 @@ int gpusim_generate_device(gpusim_ctx *ctx, int32_t first, int32_t n, void *out_
     GS_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->s_compute;
     ctx->timing = gpusim_timing{};
-    int rc = launch_range(ctx, first, n, (uint8_t *)out_device, s, true);
+    int rc = launch_range(ctx, first, n, (uint8_t *)out_device, s);
     if (rc != GPUSIM_OK)
         return rc;
     if (!stream)
@@ -573,11 +627,15 @@ static int generate_to_host(gpusim_ctx *ctx, const gpusim_epoch_table *t, uint8_
 
     // The chain kernel is latency bound (its duration is one chain, whatever the batch): run it once
     // for the whole table, then generate and copy back sub-batch by sub-batch.
+    // (upload_table drained every earlier call, so either checkpoint slot is free.)
+    const int slot = (int)(ctx->seq++ & 1u);
+    ctx->last_slot = slot;
     DeviceJob whole;
-    const SynthKernel which = plan_job(ctx, 0, n, ctx->d_out, whole);
-    GS_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->s_compute));
+    const SynthKernel which = plan_job(ctx, 0, n, ctx->d_out, whole, slot);
+    GS_CUDA(ctx, cudaEventRecord(ctx->ev_c0[slot], ctx->s_compute));
     GS_CUDA(ctx, launch_chain(whole, ctx->opt_chain_replay ? ChainAlgo::Replay : ChainAlgo::Jump, ctx->s_compute));
-    GS_CUDA(ctx, cudaEventRecord(ctx->ev_t1, ctx->s_compute));
+    GS_CUDA(ctx, cudaEventRecord(ctx->ev_c1[slot], ctx->s_compute));
+    GS_CUDA(ctx, cudaEventRecord(ctx->ev_s0[slot], ctx->s_compute));
     ctx->timing.launches += 1;
     ctx->timing.fast_path = (which != SynthKernel::Generic) ? 1 : 0;
 
@@ -589,7 +647,7 @@ static int generate_to_host(gpusim_ctx *ctx, const gpusim_epoch_table *t, uint8_
         uint8_t *dst_dev = ctx->d_out + (size_t)first * eb;
         const DeviceJob job = sub_job(ctx, whole, first, cnt, dst_dev);
         if (b > 0)
-            GS_CUDA(ctx, cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int), ctx->s_compute));
+            GS_CUDA(ctx, cudaMemsetAsync(whole.work_counter, 0, sizeof(unsigned int), ctx->s_compute));
         GS_CUDA(ctx, launch_synth(job, which, ctx->s_compute));
         ctx->timing.launches += 1;
         GS_CUDA(ctx, cudaEventRecord(ctx->ev_done[b & 1], ctx->s_compute));
@@ -607,7 +665,7 @@ static int generate_to_host(gpusim_ctx *ctx, const gpusim_epoch_table *t, uint8_
         pending_first = first;
         pending_n = cnt;
     }
-    GS_CUDA(ctx, cudaEventRecord(ctx->ev_t2, ctx->s_compute));
+    GS_CUDA(ctx, cudaEventRecord(ctx->ev_s1[slot], ctx->s_compute));
     GS_CUDA(ctx, cudaStreamSynchronize(ctx->s_copy));
     if (pending >= 0 && sink)
         if (sink(user, ctx->h_stage[pending & 1], (size_t)pending_n * eb) != 0)

@@ -22,7 +22,7 @@ namespace gpusim {
 // K1
 // ------------------------------------------------------------------------------------
 template <bool kReplay>
-__global__ void __launch_bounds__(32) k1_chain(DeviceJob job)
+__global__ void __maxnreg__(32) k1_chain(DeviceJob job)
 {
     // One warp = ONE channel slot over 32 consecutive epochs.  The host re-derives the code phase
     // from the pseudorange every epoch, but the signal is continuous, so the same satellite starts
@@ -78,6 +78,15 @@ cudaError_t launch_chain(const DeviceJob &job, ChainAlgo algo, cudaStream_t stre
     const int blocks = ((job.n_epochs + 31) / 32) * kMaxChan * (job.carrier_float ? 2 : 1);
     if (blocks == 0)
         return cudaSuccess;
+    // Same shared-memory carve-out as the synthesis kernel: an SM cannot host two kernels that ask
+    // for different L1/shared splits, and this kernel is meant to run beside the previous call's K2.
+    static const cudaError_t carve = []() {
+        cudaError_t e = cudaFuncSetAttribute(k1_chain<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(k1_chain<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        return e;
+    }();
+    (void)carve;
     if (algo == ChainAlgo::Replay)
         k1_chain<true><<<blocks, threads, 0, stream>>>(job);
     else
@@ -126,6 +135,17 @@ template <bool CF> struct K2Geom {
     static constexpr uint32_t kSecond = 8u * kThreads;               // (phs, meta) / 512*carr_phase
     static constexpr uint32_t kMeta = CF ? 16u * kThreads : 8u * kThreads + 4u;
 };
+
+// Register cap of the synthesis kernel.  Normally one block owns the SM (launch bound: 128 registers
+// INT / 168 FLOAT at 512 / 384 threads).  The "shared SM" build of the INT kernel is capped at 112:
+// that leaves 2048 of the 16384 registers of every SM sub-partition free (4 warps x 32 lanes x 112 =
+// 14336), room for two warps of the NEXT call's chain kernel (k1_chain: 32-thread blocks, 32
+// registers) beside the resident block.  At 120 nothing fits (measured: no overlap); at 112 the
+// chain kernel disappears behind the synthesis kernel, which itself gets ~4 % slower.
+constexpr int k2_max_regs(bool carrier_float, bool shared_sm)
+{
+    return shared_sm ? 112 : (carrier_float ? 168 : 128);
+}
 
 size_t synth_smem_bytes_float(int max_active)
 {
@@ -247,8 +267,8 @@ __device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows
         store_run<A, FMT, SR>(dst, acc);
 }
 
-template <class A, int FMT, int S, bool CF>
-__global__ void __launch_bounds__(K2Geom<CF>::kThreads, 1) k2_synth(DeviceJob job)
+template <class A, int FMT, int S, bool CF, bool SHARED_SM>
+__global__ void __maxnreg__(k2_max_regs(CF, SHARED_SM)) k2_synth(DeviceJob job)
 {
     typedef K2Geom<CF> G;
     constexpr int T = G::kThreads;
@@ -418,18 +438,18 @@ __global__ void __launch_bounds__(128) k2_generic(DeviceJob job)
     }
 }
 
-template <class A, int FMT, int S, bool CF>
+template <class A, int FMT, int S, bool CF, bool SHARED_SM = false>
 static cudaError_t launch_tuned_a(const DeviceJob &job, cudaStream_t stream)
 {
     constexpr int T = K2Geom<CF>::kThreads;
     const size_t smem = kSmemLut + kSmemNegw + (size_t)std::max(1, job.max_active) * K2Geom<CF>::kStride;
-    cudaError_t err = cudaFuncSetAttribute(k2_synth<A, FMT, S, CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = cudaFuncSetAttribute(k2_synth<A, FMT, S, CF, SHARED_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess)
         return err;
     const long long units = job.n_units;
     const long long warps_per_block = T / 32;
     const int blocks = (int)std::min<long long>(std::max(1, job.sm_count), (units + warps_per_block - 1) / warps_per_block);
-    k2_synth<A, FMT, S, CF><<<blocks, T, smem, stream>>>(job);
+    k2_synth<A, FMT, S, CF, SHARED_SM><<<blocks, T, smem, stream>>>(job);
     return cudaGetLastError();
 }
 
@@ -438,6 +458,8 @@ static cudaError_t launch_tuned(const DeviceJob &job, cudaStream_t stream)
 {
     if (job.carrier_float)
         return launch_tuned_a<AccF32x2, FMT, S, true>(job, stream);
+    if (S == 32 && job.accum == 1 && job.shared_sm)
+        return launch_tuned_a<AccF32x2, FMT, 32, false, true>(job, stream);
     return job.accum == 1 ? launch_tuned_a<AccF32x2, FMT, S, false>(job, stream)
                           : launch_tuned_a<AccWide, FMT, S, false>(job, stream);
 }

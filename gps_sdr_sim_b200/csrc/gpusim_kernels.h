@@ -41,6 +41,7 @@ struct DeviceJob {
     int32_t q;               // aligned layout: chunks per code period
     int32_t n_units;         // work units (32 chunks each) of the tuned kernel
     int32_t carrier_float;   // 1: FLOAT_CARR_PHASE host (double carrier phase), 0: integer carrier
+    int32_t shared_sm;       // 1: K2 build that leaves registers for the next call's K1 (see k2_max_regs)
 };
 
 enum class ChainAlgo { Jump = 0, Replay = 1 };

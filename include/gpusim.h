@@ -150,7 +150,10 @@ int gpusim_generate_epochs_to_sink(gpusim_ctx *ctx, const gpusim_epoch_table *ta
  * samples on the GPU: upload once, then generate any epoch sub-range
  * [first_epoch, first_epoch+n_epochs) of the uploaded table into device memory.
  * `stream` is a cudaStream_t (NULL = the library's own stream); the call is
- * asynchronous with respect to the host when a stream is given.
+ * asynchronous with respect to the host when a stream is given.  Calls issued
+ * back to back are pipelined: the output of call i is complete when `stream`
+ * reaches the point after call i, but the code-phase chain kernel of call i+1
+ * already runs (on a library stream) beside the synthesis kernel of call i.
  */
 int gpusim_upload_table(gpusim_ctx *ctx, const gpusim_epoch_table *table);
 int gpusim_generate_device(gpusim_ctx *ctx, int32_t first_epoch, int32_t n_epochs,
@@ -161,7 +164,9 @@ int gpusim_get_timing(const gpusim_ctx *ctx, gpusim_timing *out);
 /* Tuning / test hooks (all optional).  key/value pairs documented in DESIGN.md:
  *   "chunk"  samples per thread chunk (multiple of 32), 0 = auto
  *   "force_generic" 1 = always use the generic exact kernel
- *   "force_slow" 1 = always take the wrap-checking inner loop */
+ *   "force_slow" 1 = always take the wrap-checking inner loop
+ *   "pipeline" 1 = (default) overlap the chain kernel with the previous call's synthesis kernel
+ *              when the epoch is long enough for that to pay, 0 = never, 2 = whenever possible */
 int gpusim_set_option(gpusim_ctx *ctx, const char *key, int64_t value);
 
 /*

@@ -102,6 +102,39 @@ def test_device_resident_path_and_epoch_independence():
         assert t.synth_ms > 0 and t.chain_ms > 0
 
 
+@pytest.mark.parametrize("mode,pipeline", [(gs.CARRIER_INT, 1), (gs.CARRIER_INT, 2), (gs.CARRIER_INT, 0), (gs.CARRIER_FLOAT, 1)])
+def test_back_to_back_device_calls_overlap_safely(mode, pipeline):
+    """Consecutive generate_device calls are pipelined inside the library (the chain kernel of call
+    i+1 runs beside the synthesis kernel of call i, on alternating checkpoint sets).  Seven calls with
+    different ranges and sizes issued without any synchronisation, then a re-upload and more calls:
+    every range must equal the oracle."""
+    import torch
+    t = gs.synthetic_table(24, 260000, 9, gs.SC08, seed=11, carrier_mode=mode)
+    want = oracle_lib.generate(t)
+    eb = t.epoch_bytes
+    ranges = [(0, 24), (3, 5), (8, 16), (0, 1), (23, 1), (5, 19), (0, 24)]
+    with gs.GpuSim.for_table(t) as sim:
+        sim.set_option("pipeline", pipeline)      # 1 = overlap when the previous call is still running, 2 = always
+        sim.upload_table(t)
+        s = torch.cuda.Stream()
+        bufs = [torch.zeros(n * eb, dtype=torch.uint8, device="cuda") for _, n in ranges]
+        torch.cuda.synchronize()
+        for (first, n), buf in zip(ranges, bufs):
+            sim.generate_device(first, n, buf.data_ptr(), buf.numel(), stream=s.cuda_stream)
+        # a new table while the calls above may still be running: upload must wait for them
+        t2 = gs.synthetic_table(24, 260000, 9, gs.SC08, seed=12, carrier_mode=mode)
+        sim.upload_table(t2)
+        again = torch.zeros(4 * eb, dtype=torch.uint8, device="cuda")
+        sim.generate_device(10, 4, again.data_ptr(), again.numel(), stream=s.cuda_stream)
+        sim.generate_device(10, 4, again.data_ptr(), again.numel(), stream=s.cuda_stream)
+        s.synchronize()
+        for (first, n), buf in zip(ranges, bufs):
+            assert np.array_equal(buf.cpu().numpy(), want[first * eb:(first + n) * eb]), (first, n)
+        assert np.array_equal(again.cpu().numpy(), oracle_lib.generate(t2.slice(10, 4)))
+        tm = sim.timing()
+        assert tm.synth_ms > 0 and tm.chain_ms > 0
+
+
 @pytest.mark.parametrize("fmt", [gs.SC16, gs.SC08, gs.SC01])
 def test_synthetic_rows_sixteen_channels_extreme_ranges(fmt):
     t = gs.synthetic_table(6, 260000, 16, fmt, seed=3)

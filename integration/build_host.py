@@ -50,6 +50,14 @@ def apply_binding(src: str) -> str:
     assert "carr_phase" in body and "iq8_buff" in body and "generateNavMsg" not in body
     src = src[:start] + "\t\tGPUSIM_HOOK_EPOCH();\n" + src[end:]
 
+    # (2b) optional: the computeRange() pair of the epoch loop (gpssim.c:2165-2168) becomes a look-up
+    #      into ranges the hook computed ahead of time with the same function
+    loop = src.index("for (iumd=1; iumd<numd; iumd++)")
+    m = re.compile(r"if \(!staticLocationMode\)\s*\n\s*computeRange\(&rho, eph\[ieph\]\[sv\], &ionoutc, grx, xyz\[iumd\]\);\s*\n"
+                   r"\s*else\s*\n\s*computeRange\(&rho, eph\[ieph\]\[sv\], &ionoutc, grx, xyz\[0\]\);").search(src, loop)
+    assert m and m.start() - loop < 1000, "computeRange pair of the epoch loop not found"
+    src = src[:m.start()] + "GPUSIM_HOOK_RANGE();" + src[m.end():]
+
     # (3) open before the loop's clock starts, close before it stops
     m = re.search(r"^\s*tstart = clock\(\);", src, re.M)
     assert m

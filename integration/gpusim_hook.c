@@ -10,7 +10,8 @@
  * own fwrite on the reference's own FILE* (gpssim.c:2276/:2283/:2287).
  *
  * Environment (all optional):
- *   GPUSIM_BATCH_EPOCHS  epochs per library call            (default 256)
+ *   GPUSIM_BATCH_EPOCHS  epochs per library call, fixed     (default: 256, doubling per call up to a
+ *                        memory-derived cap of at most 4096)
  *   GPUSIM_DEVICE        CUDA device ordinal                (default 0)
  *   GPUSIM_DEVICES       number of GPUs (devices 0..n-1) to time-shard batches over (default 1):
  *                        batch b goes to device b mod n; one worker thread per GPU generates into
@@ -20,12 +21,31 @@
  *   GPUSIM_DUMP          path: also write every table row to this file
  *                        (format below) - how tests/golden/ fixtures are made
  *   GPUSIM_DRYRUN        1: record (and dump) rows, generate nothing, write nothing
+ *   GPUSIM_HOST_THREADS  host threads for the row pre-pass (default: online CPUs, at most 16; 1 = the
+ *                        reference's serial order of calls, nothing precomputed)
+ *
+ * Host pre-pass.  Producing the rows is the reference's own code and stays
+ * bit-identical; what changes is when and where it runs:
+ *   - the main thread only fills rows; generation + fwrite run on worker threads (one per GPU), so
+ *     the pre-pass of batch b+1 overlaps the GPU work of batch b;
+ *   - GPUSIM_HOOK_RANGE() replaces the computeRange() call of the epoch loop (gpssim.c:2165-2168)
+ *     by a look-up into a window of ranges computed ahead of time, in parallel over epochs, by the
+ *     reference's own computeRange() - a pure function of (ephemeris, iono, time, position); a
+ *     window never crosses a 30 s channel/ephemeris refresh (gpssim.c:2296-2345) and every look-up
+ *     re-checks time, PRN and ephemeris set, falling back to a direct call;
+ *   - FLOAT_CARR_PHASE hosts: the double carrier phase chains through every sample of the run
+ *     (gpssim.c:2245-2250); its per-epoch advance is an exact O(carrier cycles) walk that costs
+ *     ~40 us per channel and epoch.  The chains of different channels are independent, so they are
+ *     filled in per batch, one thread per channel slot, instead of inside the epoch loop.
  */
+#define _GNU_SOURCE
 #include <pthread.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
+#include <unistd.h>
 
 #include "gpssim.h"
 #include "gpusim_hook.h"
@@ -52,9 +72,53 @@ typedef struct
 	double *carr_phase_f;
 	int32_t *iword; /* diagnostics only (dump) */
 	int32_t *ibit;
+	double *carr_init; /* FLOAT hosts: carrier phase of a freshly allocated channel, or HOOK_CONTINUE */
 } cols_t;
 
-/* multi-GPU pipeline: a ring of batch slots; slot states advance FREE -> QUEUED -> DONE -> FREE */
+/* the reference's own functions (gpssim.c:789, :1253; external linkage, not declared in gpssim.h) */
+extern void computeRange(range_t *rho, ephem_t eph, ionoutc_t *ionoutc, gpstime_t g, double xyz[]);
+extern gpstime_t incGpsTime(gpstime_t g0, double dt);
+
+/* FLOAT hosts: value left in chan[i].carr_phase after an epoch was recorded.  The reference only ever
+ * stores values in [0,1) there (gpssim.c:1622, :2245-2250), so anything else found at the next epoch
+ * means allocateChannel() has (re)started the channel with a fresh phase. */
+#define HOOK_CONTINUE (-1.0)
+
+/* ---- fork/join pool for the host pre-pass ------------------------------------------------ */
+typedef void (*pool_fn)(void *arg, int item);
+typedef struct
+{
+	int n; /* helper threads (the caller works too) */
+	pthread_t *threads;
+	pthread_mutex_t mu;
+	pthread_cond_t cv_job, cv_done;
+	pool_fn fn;
+	void *arg;
+	int n_items;
+	int next;    /* next unclaimed item (atomic) */
+	int running; /* helpers still inside the current job */
+	long gen;    /* job generation */
+	int stop;
+} pool_t;
+
+/* look-ahead window of computeRange() results */
+#define RA_WIN 512
+typedef struct
+{
+	int enabled;
+	int first, count;        /* epochs [first, first+count) of the host's iumd counter */
+	const ephem_t *eph_set;  /* eph[ieph] the window was computed with */
+	ionoutc_t *ionoutc;
+	double (*xyz)[3];        /* user motion, NULL in static mode */
+	double *xyz0;
+	int prn[MAX_CHAN];
+	gpstime_t g[RA_WIN];
+	range_t *rho;            /* [RA_WIN][MAX_CHAN] */
+	long hits, direct, windows;
+	int short_windows;       /* consecutive windows that served a single epoch */
+} lookahead_t;
+
+/* GPU pipeline: a ring of batch slots; slot states advance FREE -> QUEUED -> DONE -> FREE */
 #define HOOK_MAX_DEV 16
 enum { SLOT_FREE = 0, SLOT_QUEUED = 1, SLOT_DONE = 2 };
 typedef struct
@@ -87,7 +151,13 @@ struct gpusim_hook
 	cols_t batch;
 	cols_t dump;
 	long epochs_done;
-	/* multi-GPU (ndev > 1) */
+	double t_open, t_wait, t_chains, t_ranges; /* wall clock [s]: start; main thread waiting for a free slot, walking carrier chains, computing range windows */
+	int flush_at, cap_max; /* epochs per batch: current size (doubles per batch) and its cap */
+	int host_threads;
+	pool_t pool;
+	lookahead_t ra;
+	double cph[MAX_CHAN]; /* FLOAT hosts: carrier phase of every slot at the next unfilled epoch */
+	/* GPU pipeline: ndev workers (sink mode when ndev == 1: the worker fwrites, no writer thread) */
 	int ndev, nslots;
 	slot_t *slots;
 	worker_t workers[HOOK_MAX_DEV];
@@ -97,6 +167,13 @@ struct gpusim_hook
 	long seq_filled; /* batches handed to the workers so far */
 	int finishing;   /* no more batches will be queued */
 };
+
+static double now_s(void)
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
 
 static void die(const char *what, const char *detail)
 {
@@ -132,6 +209,7 @@ static void cols_reserve(cols_t *c, int epochs)
 	c->carr_phase_f = xrealloc(c->carr_phase_f, rows * sizeof(double));
 	c->iword = xrealloc(c->iword, rows * sizeof(int32_t));
 	c->ibit = xrealloc(c->ibit, rows * sizeof(int32_t));
+	c->carr_init = xrealloc(c->carr_init, rows * sizeof(double));
 	c->cap = epochs;
 }
 
@@ -139,7 +217,7 @@ static void cols_free(cols_t *c)
 {
 	free(c->prn); free(c->f_code); free(c->code_phase); free(c->icode);
 	free(c->nav_bits); free(c->gain); free(c->carr_phasestep); free(c->carr_phase);
-	free(c->f_carr); free(c->carr_phase_f); free(c->iword); free(c->ibit);
+	free(c->f_carr); free(c->carr_phase_f); free(c->iword); free(c->ibit); free(c->carr_init);
 	memset(c, 0, sizeof(*c));
 }
 
@@ -151,7 +229,7 @@ static void cols_append(cols_t *dst, const cols_t *src, int e)
 	d = (size_t)dst->n * MAX_CHAN;
 #define CP(f) memcpy(dst->f + d, src->f + o, MAX_CHAN * sizeof(*dst->f))
 	CP(prn); CP(f_code); CP(code_phase); CP(icode); CP(nav_bits); CP(gain);
-	CP(carr_phasestep); CP(carr_phase); CP(f_carr); CP(carr_phase_f); CP(iword); CP(ibit);
+	CP(carr_phasestep); CP(carr_phase); CP(f_carr); CP(carr_phase_f); CP(iword); CP(ibit); CP(carr_init);
 #undef CP
 	dst->n++;
 }
@@ -180,7 +258,215 @@ static void table_of(const cols_t *c, gpusim_epoch_table *t)
 	t->carr_phase_f = c->carr_phase_f;
 }
 
-/* ---- multi-GPU pipeline ------------------------------------------------------------------ */
+/* ---- fork/join pool ---------------------------------------------------------------------- */
+static void pool_work(pool_t *p)
+{
+	for (;;)
+	{
+		int item = __atomic_fetch_add(&p->next, 1, __ATOMIC_RELAXED);
+		if (item >= p->n_items)
+			return;
+		p->fn(p->arg, item);
+	}
+}
+
+static void *pool_main(void *arg)
+{
+	pool_t *p = (pool_t *)arg;
+	long seen = 0;
+	pthread_mutex_lock(&p->mu);
+	for (;;)
+	{
+		while (!p->stop && p->gen == seen)
+			pthread_cond_wait(&p->cv_job, &p->mu);
+		if (p->stop)
+			break;
+		seen = p->gen;
+		pthread_mutex_unlock(&p->mu);
+		pool_work(p);
+		pthread_mutex_lock(&p->mu);
+		if (--p->running == 0)
+			pthread_cond_signal(&p->cv_done);
+	}
+	pthread_mutex_unlock(&p->mu);
+	return NULL;
+}
+
+static void pool_start(pool_t *p, int helpers)
+{
+	int i;
+	memset(p, 0, sizeof(*p));
+	pthread_mutex_init(&p->mu, NULL);
+	pthread_cond_init(&p->cv_job, NULL);
+	pthread_cond_init(&p->cv_done, NULL);
+	if (helpers <= 0)
+		return;
+	p->threads = xrealloc(NULL, (size_t)helpers * sizeof(pthread_t));
+	for (i = 0; i < helpers; i++)
+	{
+		if (pthread_create(&p->threads[i], NULL, pool_main, p) != 0)
+			break;
+		p->n++;
+	}
+}
+
+/* run fn(arg, 0..n_items-1) on the helpers and the calling thread; returns when all are done */
+static void pool_run(pool_t *p, pool_fn fn, void *arg, int n_items)
+{
+	int i;
+	if (p->n == 0 || n_items <= 1)
+	{
+		for (i = 0; i < n_items; i++)
+			fn(arg, i);
+		return;
+	}
+	pthread_mutex_lock(&p->mu);
+	p->fn = fn;
+	p->arg = arg;
+	p->n_items = n_items;
+	__atomic_store_n(&p->next, 0, __ATOMIC_RELAXED);
+	p->running = p->n;
+	p->gen++;
+	pthread_cond_broadcast(&p->cv_job);
+	pthread_mutex_unlock(&p->mu);
+	pool_work(p);
+	pthread_mutex_lock(&p->mu);
+	while (p->running > 0)
+		pthread_cond_wait(&p->cv_done, &p->mu);
+	pthread_mutex_unlock(&p->mu);
+}
+
+static void pool_stop(pool_t *p)
+{
+	int i;
+	pthread_mutex_lock(&p->mu);
+	p->stop = 1;
+	pthread_cond_broadcast(&p->cv_job);
+	pthread_mutex_unlock(&p->mu);
+	for (i = 0; i < p->n; i++)
+		pthread_join(p->threads[i], NULL);
+	free(p->threads);
+	p->threads = NULL;
+	p->n = 0;
+}
+
+/* ---- FLOAT hosts: the carrier-phase chains of one batch, one channel slot per work item ---- */
+#ifdef FLOAT_CARR_PHASE
+static void carrier_slot(void *arg, int slot)
+{
+	gpusim_hook *h = (gpusim_hook *)arg;
+	cols_t *b = &h->batch;
+	double cph = h->cph[slot];
+	int e;
+	for (e = 0; e < b->n; e++)
+	{
+		size_t o = (size_t)e * MAX_CHAN + slot;
+		if (b->prn[o] <= 0)
+			continue;
+		if (b->carr_init[o] != HOOK_CONTINUE)
+			cph = b->carr_init[o]; /* allocateChannel() started this channel here, gpssim.c:1622 */
+		b->carr_phase_f[o] = cph;
+		/* the exact result of the N updates of gpssim.c:2245-2250 */
+		cph = gpusim_advance_carrier_f64(cph, b->f_carr[o], h->delt, h->N);
+	}
+	h->cph[slot] = cph;
+}
+#endif
+
+static void fill_carrier_chains(gpusim_hook *h)
+{
+#ifdef FLOAT_CARR_PHASE
+	pool_run(&h->pool, carrier_slot, h, MAX_CHAN);
+#else
+	(void)h;
+#endif
+}
+
+/* ---- computeRange() look-ahead ------------------------------------------------------------ */
+#define RA_GROUP 4 /* epochs per work item */
+static void lookahead_item(void *arg, int item)
+{
+	lookahead_t *ra = &((gpusim_hook *)arg)->ra;
+	int k, i;
+	for (k = item * RA_GROUP; k < (item + 1) * RA_GROUP && k < ra->count; k++)
+		for (i = 0; i < MAX_CHAN; i++)
+			if (ra->prn[i] > 0)
+				computeRange(&ra->rho[(size_t)k * MAX_CHAN + i], ra->eph_set[ra->prn[i] - 1], ra->ionoutc, ra->g[k],
+				             ra->xyz != NULL ? ra->xyz[ra->first + k] : ra->xyz0);
+}
+
+static void lookahead_build(gpusim_hook *h, int iumd, int numd, const channel_t *chan, const ephem_t *eph_set,
+                            ionoutc_t *ionoutc, gpstime_t grx, double (*xyz)[3], double *xyz0)
+{
+	lookahead_t *ra = &h->ra;
+	gpstime_t g = grx;
+	int i, k;
+
+	if (ra->rho == NULL)
+		ra->rho = xrealloc(NULL, (size_t)RA_WIN * MAX_CHAN * sizeof(range_t));
+	/* a window that served one epoch only means the assumptions below do not hold for this host */
+	if (ra->windows > 0 && ra->count > 1 && iumd == ra->first + 1)
+	{
+		if (++ra->short_windows >= 8)
+		{
+			ra->enabled = 0;
+			ra->count = 0;
+			return;
+		}
+	}
+	else
+		ra->short_windows = 0;
+
+	ra->first = iumd;
+	ra->eph_set = eph_set;
+	ra->ionoutc = ionoutc;
+	ra->xyz = xyz;
+	ra->xyz0 = xyz0;
+	for (i = 0; i < MAX_CHAN; i++)
+		ra->prn[i] = chan[i].prn;
+	/* epochs up to and including the one whose end refreshes channels / ephemerides
+	 * (gpssim.c:2294-2296); receiver time advances exactly as the host will advance it (:2348) */
+	ra->count = 0;
+	for (k = 0; k < RA_WIN && iumd + k < numd; k++)
+	{
+		ra->g[k] = g;
+		ra->count = k + 1;
+		if ((int)(g.sec * 10.0 + 0.5) % 300 == 0)
+			break;
+		g = incGpsTime(g, 0.1);
+	}
+	ra->windows++;
+	{
+		const double t0 = now_s();
+		pool_run(&h->pool, lookahead_item, h, (ra->count + RA_GROUP - 1) / RA_GROUP);
+		h->t_ranges += now_s() - t0;
+	}
+}
+
+void gpusim_hook_range(gpusim_hook *h, range_t *rho, int slot, int iumd, int numd, const channel_t *chan,
+                       const ephem_t *eph_set, ionoutc_t *ionoutc, gpstime_t grx, double (*xyz)[3], double *xyz0)
+{
+	lookahead_t *ra = &h->ra;
+	int attempt;
+	for (attempt = 0; ra->enabled && attempt < 2; attempt++)
+	{
+		int k = iumd - ra->first;
+		if (k >= 0 && k < ra->count && ra->eph_set == eph_set && ra->ionoutc == ionoutc && ra->xyz == xyz &&
+		    ra->xyz0 == xyz0 && ra->prn[slot] == chan[slot].prn && ra->g[k].week == grx.week && ra->g[k].sec == grx.sec)
+		{
+			*rho = ra->rho[(size_t)k * MAX_CHAN + slot];
+			ra->hits++;
+			return;
+		}
+		if (attempt == 0)
+			lookahead_build(h, iumd, numd, chan, eph_set, ionoutc, grx, xyz, xyz0);
+	}
+	/* the reference's own call, gpssim.c:2165-2168 */
+	ra->direct++;
+	computeRange(rho, eph_set[chan[slot].prn - 1], ionoutc, grx, xyz != NULL ? xyz[iumd] : xyz0);
+}
+
+/* ---- GPU pipeline: workers generate, batches are written strictly in order --------------------- */
 static void *worker_main(void *arg)
 {
 	worker_t *w = (worker_t *)arg;
@@ -202,12 +488,15 @@ static void *worker_main(void *arg)
 		pthread_mutex_unlock(&h->mu);
 
 		table_of(&s->rows, &t);
-		rc = gpusim_generate_epochs(w->ctx, &t, s->out, (size_t)h->batch.cap * gpusim_epoch_bytes(w->ctx));
+		if (h->ndev == 1) /* one GPU: this thread is also the (ordered) writer, from the library's staging buffers */
+			rc = gpusim_generate_epochs_to_sink(w->ctx, &t, sink_fwrite, h);
+		else
+			rc = gpusim_generate_epochs(w->ctx, &t, s->out, (size_t)h->cap_max * gpusim_epoch_bytes(w->ctx));
 		if (rc != GPUSIM_OK)
 			die("GPU sample generation failed", gpusim_last_error(w->ctx));
 
 		pthread_mutex_lock(&h->mu);
-		s->state = SLOT_DONE;
+		s->state = h->ndev == 1 ? SLOT_FREE : SLOT_DONE;
 		pthread_cond_broadcast(&h->cv);
 		pthread_mutex_unlock(&h->mu);
 	}
@@ -247,9 +536,11 @@ static void queue_batch(gpusim_hook *h)
 {
 	slot_t *s = &h->slots[h->seq_filled % h->nslots];
 	cols_t tmp;
+	const double t0 = now_s();
 	pthread_mutex_lock(&h->mu);
 	while (s->state != SLOT_FREE)
 		pthread_cond_wait(&h->cv, &h->mu);
+	h->t_wait += now_s() - t0;
 	tmp = s->rows;
 	s->rows = h->batch;
 	h->batch = tmp;
@@ -262,30 +553,36 @@ static void queue_batch(gpusim_hook *h)
 
 static void flush_batch(gpusim_hook *h)
 {
-	gpusim_epoch_table t;
-	int rc;
+	int e;
 
 	if (h->batch.n == 0)
 		return;
 
-	if (!h->dryrun && h->ndev > 1)
 	{
-		h->epochs_done += h->batch.n;
-		queue_batch(h);
-		return;
+		const double t0 = now_s();
+		fill_carrier_chains(h);
+		h->t_chains += now_s() - t0;
 	}
-
-	if (!h->dryrun)
-	{
-		table_of(&h->batch, &t);
-
-		rc = gpusim_generate_epochs_to_sink(h->ctx, &t, sink_fwrite, h);
-		if (rc != GPUSIM_OK)
-			die("GPU sample generation failed", gpusim_last_error(h->ctx));
-	}
+	if (h->dump_path != NULL)
+		for (e = 0; e < h->batch.n; e++)
+			cols_append(&h->dump, &h->batch, e);
 
 	h->epochs_done += h->batch.n;
-	h->batch.n = 0;
+	if (!h->dryrun)
+		queue_batch(h); /* generation and fwrite happen on the worker / writer threads */
+	else
+		h->batch.n = 0;
+}
+
+static int default_host_threads(void)
+{
+	long n = sysconf(_SC_NPROCESSORS_ONLN);
+	cpu_set_t set;
+	if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0 && CPU_COUNT(&set) < n)
+		n = CPU_COUNT(&set);
+	if (n < 1)
+		n = 1;
+	return n > 16 ? 16 : (int)n;
 }
 
 gpusim_hook *gpusim_hook_open(int iq_buff_size, double delt, int data_format, FILE *fp)
@@ -306,13 +603,8 @@ gpusim_hook *gpusim_hook_open(int iq_buff_size, double delt, int data_format, FI
 #else
 	h->carrier_mode = GPUSIM_CARRIER_INT;
 #endif
-	if ((s = getenv("GPUSIM_BATCH_EPOCHS")) != NULL && atoi(s) > 0)
-		batch = atoi(s);
 	h->dryrun = ((s = getenv("GPUSIM_DRYRUN")) != NULL && atoi(s) != 0);
 	h->dump_path = getenv("GPUSIM_DUMP");
-
-	cols_reserve(&h->batch, batch);
-	h->batch.cap = batch; /* fixed: flush when full */
 
 	h->ndev = 1;
 	if ((s = getenv("GPUSIM_DEVICE_LIST")) != NULL && *s)
@@ -335,55 +627,76 @@ gpusim_hook *gpusim_hook_open(int iq_buff_size, double delt, int data_format, FI
 			h->workers[d].device = d;
 	}
 
+	/* Epochs per library call.  Every call costs one code-phase chain kernel, whose duration (~0.5 ms)
+	 * is the latency of one chain whatever the batch, plus a few synchronisations: long runs want
+	 * large batches, the first bytes want a small one.  So batches start at 256 epochs and double up
+	 * to a cap set by memory (device output per call; page-locked ring buffers with several GPUs). */
+	{
+		const double eb = data_format == 16 ? 4.0 * iq_buff_size : data_format == 8 ? 2.0 * iq_buff_size : iq_buff_size / 4.0;
+		const double budget = h->ndev > 1 ? 256.0 * 1048576.0 : 2048.0 * 1048576.0;
+		double cap = budget / (eb > 1.0 ? eb : 1.0);
+		batch = cap > 4096.0 ? 4096 : cap < 32.0 ? 32 : (int)cap;
+		h->flush_at = batch < 256 ? batch : 256;
+		if ((s = getenv("GPUSIM_BATCH_EPOCHS")) != NULL && atoi(s) > 0)
+			h->flush_at = batch = atoi(s); /* fixed size */
+		h->cap_max = batch;
+	}
+	cols_reserve(&h->batch, batch);
+	h->batch.cap = batch;
+
+	h->host_threads = default_host_threads();
+	if ((s = getenv("GPUSIM_HOST_THREADS")) != NULL && atoi(s) > 0)
+		h->host_threads = atoi(s) > 64 ? 64 : atoi(s);
+	pool_start(&h->pool, h->host_threads - 1);
+	h->ra.enabled = h->pool.n > 0;
+
 	if (!h->dryrun)
 	{
 		gpusim_config cfg;
 		int rc, d;
 		memset(&cfg, 0, sizeof(cfg));
 		cfg.abi_version = GPUSIM_ABI_VERSION;
-		cfg.device = (s = getenv("GPUSIM_DEVICE")) != NULL ? atoi(s) : 0;
 		cfg.samples_per_epoch = iq_buff_size;
 		cfg.data_format = data_format;
 		cfg.carrier_mode = h->carrier_mode;
 		cfg.max_batch_epochs = batch;
 		cfg.delt = delt;
-		if (h->ndev == 1)
+		if (h->ndev == 1 && getenv("GPUSIM_DEVICE_LIST") == NULL)
+			h->workers[0].device = (s = getenv("GPUSIM_DEVICE")) != NULL ? atoi(s) : 0;
+
+		/* time-sharding over GPUs: epochs are independent given their rows, no exchange needed */
+		pthread_mutex_init(&h->mu, NULL);
+		pthread_cond_init(&h->cv, NULL);
+		h->nslots = 2 * h->ndev;
+		h->slots = calloc((size_t)h->nslots, sizeof(slot_t));
+		if (h->slots == NULL)
+			die("gpusim hook out of memory", NULL);
+		for (d = 0; d < h->ndev; d++)
 		{
-			rc = gpusim_create(&cfg, &h->ctx);
+			cfg.device = h->workers[d].device;
+			rc = gpusim_create(&cfg, &h->workers[d].ctx);
 			if (rc != GPUSIM_OK)
 				die("Failed to initialise the GPU sample generator", gpusim_last_error(NULL));
+			h->workers[d].h = h;
+			h->workers[d].index = d;
 		}
-		else
+		for (d = 0; d < h->nslots; d++)
 		{
-			/* time-sharding over GPUs: epochs are independent given their rows, no exchange needed */
-			pthread_mutex_init(&h->mu, NULL);
-			pthread_cond_init(&h->cv, NULL);
-			h->nslots = 2 * h->ndev;
-			h->slots = calloc((size_t)h->nslots, sizeof(slot_t));
-			if (h->slots == NULL)
-				die("gpusim hook out of memory", NULL);
-			for (d = 0; d < h->ndev; d++)
+			cols_reserve(&h->slots[d].rows, batch);
+			h->slots[d].rows.cap = batch;
+			if (h->ndev > 1)
 			{
-				cfg.device = h->workers[d].device;
-				rc = gpusim_create(&cfg, &h->workers[d].ctx);
-				if (rc != GPUSIM_OK)
-					die("Failed to initialise the GPU sample generator", gpusim_last_error(NULL));
-				h->workers[d].h = h;
-				h->workers[d].index = d;
-			}
-			for (d = 0; d < h->nslots; d++)
-			{
-				cols_reserve(&h->slots[d].rows, batch);
-				h->slots[d].rows.cap = batch;
 				h->slots[d].out = gpusim_host_alloc((size_t)batch * gpusim_epoch_bytes(h->workers[0].ctx));
 				if (h->slots[d].out == NULL)
 					die("Failed to allocate page-locked output buffers", NULL);
 			}
-			for (d = 0; d < h->ndev; d++)
-				pthread_create(&h->workers[d].thread, NULL, worker_main, &h->workers[d]);
-			pthread_create(&h->writer, NULL, writer_main, h);
 		}
+		for (d = 0; d < h->ndev; d++)
+			pthread_create(&h->workers[d].thread, NULL, worker_main, &h->workers[d]);
+		if (h->ndev > 1)
+			pthread_create(&h->writer, NULL, writer_main, h);
 	}
+	h->t_open = now_s();
 	return h;
 }
 
@@ -401,7 +714,7 @@ void gpusim_hook_epoch(gpusim_hook *h, channel_t *chan, const int *gain)
 			b->f_code[o] = 0.0; b->code_phase[o] = 0.0; b->icode[o] = 0;
 			b->nav_bits[o] = 0; b->gain[o] = 0; b->carr_phasestep[o] = 0;
 			b->carr_phase[o] = 0; b->f_carr[o] = 0.0; b->carr_phase_f[o] = 0.0;
-			b->iword[o] = 0; b->ibit[o] = 0;
+			b->iword[o] = 0; b->ibit[o] = 0; b->carr_init[o] = 0.0;
 			continue;
 		}
 
@@ -418,25 +731,28 @@ void gpusim_hook_epoch(gpusim_hook *h, channel_t *chan, const int *gain)
 #ifdef FLOAT_CARR_PHASE
 		b->carr_phasestep[o] = 0;
 		b->carr_phase[o] = 0;
-		b->carr_phase_f[o] = chan[i].carr_phase;
-		/* The double carrier phase chains through every sample of every epoch (gpssim.c:2245-2250);
-		 * keep the host's copy exact: the library walks the N updates in O(carrier cycles). */
-		chan[i].carr_phase = gpusim_advance_carrier_f64(chan[i].carr_phase, chan[i].f_carr, h->delt, h->N);
+		/* The double carrier phase chains through every sample of every epoch (gpssim.c:2245-2250).
+		 * Only note where a chain (re)starts; fill_carrier_chains() walks the chains of the whole
+		 * batch, channel slots in parallel, before the batch is handed to the GPU. */
+		b->carr_phase_f[o] = 0.0;
+		b->carr_init[o] = chan[i].carr_phase;
+		chan[i].carr_phase = HOOK_CONTINUE;
 #else
 		b->carr_phasestep[o] = chan[i].carr_phasestep;
 		b->carr_phase[o] = chan[i].carr_phase;
 		b->carr_phase_f[o] = 0.0;
+		b->carr_init[o] = 0.0;
 		/* N times "carr_phase += carr_phasestep" on an unsigned int (gpssim.c:2252) */
 		chan[i].carr_phase += (unsigned int)h->N * (unsigned int)chan[i].carr_phasestep;
 #endif
 	}
 
-	if (h->dump_path != NULL)
-		cols_append(&h->dump, b, b->n);
-
 	b->n++;
-	if (b->n >= b->cap)
+	if (b->n >= h->flush_at)
+	{
 		flush_batch(h);
+		h->flush_at = 2 * h->flush_at < h->cap_max ? 2 * h->flush_at : h->cap_max;
+	}
 }
 
 /*
@@ -479,8 +795,9 @@ static void write_dump(const gpusim_hook *h)
 
 void gpusim_hook_close(gpusim_hook *h)
 {
+	const char *v;
 	flush_batch(h);
-	if (!h->dryrun && h->ndev > 1)
+	if (!h->dryrun)
 	{
 		int d;
 		pthread_mutex_lock(&h->mu);
@@ -489,20 +806,27 @@ void gpusim_hook_close(gpusim_hook *h)
 		pthread_mutex_unlock(&h->mu);
 		for (d = 0; d < h->ndev; d++)
 			pthread_join(h->workers[d].thread, NULL);
-		pthread_join(h->writer, NULL);
+		if (h->ndev > 1)
+			pthread_join(h->writer, NULL);
 		for (d = 0; d < h->ndev; d++)
 			gpusim_destroy(h->workers[d].ctx);
 		for (d = 0; d < h->nslots; d++)
 		{
 			cols_free(&h->slots[d].rows);
-			gpusim_host_free(h->slots[d].out);
+			if (h->slots[d].out != NULL)
+				gpusim_host_free(h->slots[d].out);
 		}
 		free(h->slots);
 	}
+	pool_stop(&h->pool);
+	if ((v = getenv("GPUSIM_VERBOSE")) != NULL && atoi(v) != 0)
+		fprintf(stderr, "\ngpusim hook: %ld epochs, %d host threads, range look-ahead: %ld windows, %ld hits, %ld direct calls\n"
+		                "gpusim hook: %.3f s from open to close; main thread: %.3f s range windows, %.3f s carrier chains, %.3f s waiting for the GPU pipeline; batches up to %d epochs\n",
+		        h->epochs_done, h->host_threads, h->ra.windows, h->ra.hits, h->ra.direct,
+		        now_s() - h->t_open, h->t_ranges, h->t_chains, h->t_wait, h->cap_max);
 	if (h->dump_path != NULL)
 		write_dump(h);
-	if (h->ctx != NULL)
-		gpusim_destroy(h->ctx);
+	free(h->ra.rho);
 	cols_free(&h->batch);
 	cols_free(&h->dump);
 	free(h);

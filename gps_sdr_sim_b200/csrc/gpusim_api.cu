@@ -72,6 +72,7 @@ struct gpusim_ctx {
 
     // options
     int opt_chunk = 0, opt_force_generic = 0, opt_force_slow = 0, opt_chain_replay = 0, opt_accum = 1, opt_layout = 0, opt_pipeline = 1;
+    int opt_direct_first_mb = 16, opt_direct_mb = 64; // sub-batch sizes when copying straight into the caller's buffer
 
     gpusim_timing timing{};
 };
@@ -477,6 +478,8 @@ int gpusim_set_option(gpusim_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "accum")) ctx->opt_accum = (int)value;
     else if (!strcmp(key, "layout")) ctx->opt_layout = (int)value;
     else if (!strcmp(key, "pipeline")) ctx->opt_pipeline = (int)value;
+    else if (!strcmp(key, "direct_first_mb")) ctx->opt_direct_first_mb = (int)std::max<int64_t>(1, value);
+    else if (!strcmp(key, "direct_mb")) ctx->opt_direct_mb = (int)std::max<int64_t>(1, value);
     else return fail(ctx, GPUSIM_ERR_ARG, "unknown option '%s'", key);
     return GPUSIM_OK;
 }
@@ -623,7 +626,12 @@ static int generate_to_host(gpusim_ctx *ctx, const gpusim_epoch_table *t, uint8_
     const size_t eb = ctx->epoch_bytes;
     if (n == 0 || eb == 0)
         return GPUSIM_OK;
-    const int sub = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, kStageBytes / eb));
+    // sub-batch sizes in epochs: staging buffers bound them in sink mode; straight into the caller's
+    // buffer the first one is small (the copy engine starts early) and the rest large (fewer copies)
+    const size_t sub_bytes = sink ? kStageBytes : ((size_t)ctx->opt_direct_mb << 20);
+    const size_t first_bytes = sink ? kStageBytes : ((size_t)ctx->opt_direct_first_mb << 20);
+    const int sub = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, sub_bytes / eb));
+    const int sub_first = (int)std::max<size_t>(1, std::min<size_t>((size_t)sub, first_bytes / eb));
 
     // The chain kernel is latency bound (its duration is one chain, whatever the batch): run it once
     // for the whole table, then generate and copy back sub-batch by sub-batch.
@@ -642,8 +650,8 @@ static int generate_to_host(gpusim_ctx *ctx, const gpusim_epoch_table *t, uint8_
     int pending = -1; // sub-batch whose copy has been issued but not yet delivered
     int pending_first = 0, pending_n = 0;
     int b = 0;
-    for (int first = 0; first < n; first += sub, b++) {
-        const int cnt = std::min(sub, n - first);
+    for (int first = 0, cnt = 0; first < n; first += cnt, b++) {
+        cnt = std::min(b == 0 ? sub_first : sub, n - first);
         uint8_t *dst_dev = ctx->d_out + (size_t)first * eb;
         const DeviceJob job = sub_job(ctx, whole, first, cnt, dst_dev);
         if (b > 0)

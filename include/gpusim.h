@@ -165,6 +165,7 @@ int gpusim_get_timing(const gpusim_ctx *ctx, gpusim_timing *out);
  *   "chunk"  samples per thread chunk (multiple of 32), 0 = auto
  *   "force_generic" 1 = always use the generic exact kernel
  *   "force_slow" 1 = always take the wrap-checking inner loop
+ *   "direct_first_mb", "direct_mb" sub-batch sizes (MiB) of gpusim_generate_epochs (default 16, 64)
  *   "pipeline" 1 = (default) overlap the chain kernel with the previous call's synthesis kernel
  *              when the epoch is long enough for that to pay, 0 = never, 2 = whenever possible */
 int gpusim_set_option(gpusim_ctx *ctx, const char *key, int64_t value);

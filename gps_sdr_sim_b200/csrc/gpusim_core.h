@@ -539,19 +539,10 @@ GS_HD void synth_wrap(typename A::acc_t (&acc)[S], ChanState &st, const double d
 // advanced by RN(f_carr*delt) per sample and wrapped both ways (gpssim.c:2245-2250), the table index
 // is floor(carr_phase*512) (gpssim.c:2200).  The device keeps cph = 512*carr_phase (an exact
 // power-of-two rescaling: every rounding commutes with it), so the index is floor(cph), again taken
-// with one round-down magic add: the low word of (cph + 2^45) is floor(cph*128) = index<<7 plus 7
-// fraction bits, i.e. already the byte offset into the replicated table once masked.
+// with one round-down magic add (carrier_index).
 // =====================================================================================
 constexpr double kCarrMod = 512.0;
 
-GS_HD uint32_t carrier_offset_bits(double cph) // floor(cph * 128), cph in [0, 512)
-{
-#ifdef __CUDA_ARCH__
-    return (uint32_t)__double2loint(__dadd_rd(cph, 35184372088832.0)); // 2^45
-#else
-    return (uint32_t)(int64_t)__builtin_floor(cph * 128.0);
-#endif
-}
 GS_HD double carrier_step(double cph, const double dc) // gpssim.c:2245-2250, scaled by 512
 {
     cph = dadd(cph, dc);
@@ -568,6 +559,18 @@ template <bool kFalling>
 GS_HD double carrier_step_signed(double cph, const double dc)
 {
     cph = dadd(cph, dc);
+#ifdef __CUDA_ARCH__
+    // The wrap as "add -512 or -0.0" chosen by an INTEGER test of the upper word: one compare and one
+    // select on the ALU pipe and one DADD, instead of the compiler's DADD + DSETP + two FSEL (it
+    // computes cph -+ 512 unconditionally and selects both halves).  Rising: cph in [0,1024), so
+    // cph >= 512 <=> upper word >= 0x40800000.  Falling: cph in (-512,512) and never -0.0 (an exact
+    // zero sum is +0.0 in round-to-nearest), so cph < 0 <=> sign bit.  x + (-0.0) == x for every x.
+    const int hi = __double2hiint(cph);
+    if (kFalling)
+        cph = __dadd_rn(cph, __hiloint2double(hi < 0 ? 0x40800000 : 0, 0));
+    else
+        cph = __dadd_rn(cph, __hiloint2double(hi >= 0x40800000 ? (int)0xC0800000u : (int)0x80000000u, 0));
+#else
     if (kFalling) {
         if (cph < 0.0)
             cph = dadd(cph, kCarrMod);
@@ -575,6 +578,7 @@ GS_HD double carrier_step_signed(double cph, const double dc)
         if (cph >= kCarrMod)
             cph = dadd(cph, -kCarrMod);
     }
+#endif
     return cph;
 }
 
@@ -585,12 +589,38 @@ struct ChanStateF {
     int32_t bitk;  // data bits consumed since the row
 };
 
-template <class A>
-GS_HD typename A::tab_t lut_at_f(const typename A::tab_t *lut, uint32_t fl, uint32_t t, uint32_t lane_off)
+// floor(cph) for cph in [0, 512): the table index of gpssim.c:2200, again one round-down magic add
+GS_HD uint32_t carrier_index(double cph)
 {
-    // chip sign = half a cycle = bit 8 of the index = bit 15 of the offset; t has the chip in bit 31
-    const uint32_t off = ((fl ^ (t >> 16)) & 0xff80u) | lane_off;
-    return *reinterpret_cast<const typename A::tab_t *>(reinterpret_cast<const char *>(lut) + off);
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__double2loint(__dadd_rd(cph, 4503599627370496.0)); // 2^52
+#else
+    return (uint32_t)(int64_t)__builtin_floor(cph);
+#endif
+}
+
+// Table entry for index idx (0..511) with the chip sign applied: the chip sign is half a cycle, i.e.
+// bit 8 of the index; t8 carries the current (inverted) chip in bit 8 (other bits are junk).
+// Device: the byte address (index*128 + this lane's replica) is ONE integer multiply-add on the FMA
+// pipe - the ALU pipe, the busiest one, only does the xor - and the load goes through a 32-bit
+// shared-window address.
+template <class A>
+GS_HD typename A::tab_t lut_at_f(const typename A::tab_t *lut, uint32_t idx, uint32_t t8, uint32_t lane_off)
+{
+    const uint32_t p = idx ^ (t8 & 0x100u);
+#ifdef __CUDA_ARCH__
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(lut) + lane_off; // loop invariant
+    uint32_t addr;
+    asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(addr) : "r"(p), "r"(base));
+    typename A::tab_t v;
+    if (sizeof(typename A::tab_t) == 8)
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(*reinterpret_cast<uint64_t *>(&v)) : "r"(addr));
+    else
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(*reinterpret_cast<uint32_t *>(&v)) : "r"(addr));
+    return v;
+#else
+    return *reinterpret_cast<const typename A::tab_t *>(reinterpret_cast<const char *>(lut) + ((p << 7) | lane_off));
+#endif
 }
 
 template <class A, int S, bool kFalling>
@@ -602,11 +632,13 @@ GS_HD void synth_fast_f(typename A::acc_t (&acc)[S], ChanStateF &st, const doubl
     const int c0 = (int)x;
     const double magic = 4503599627370496.0 - (double)c0;
     const typename A::gain_t g = A::make_gain(signed_gain);
+    // the window as a 64-bit value win << 9: shifted left by the chips advanced, bit 8 of the upper
+    // word is the current chip (bit 31 - adv of win) - one funnel shift per sample
+    const uint32_t wlo = win << 9, whi = win >> 23;
 #pragma unroll
     for (int j = 0; j < S; j++) {
         const uint32_t adv = chips_since(x, magic);
-        // (win << adv) has the current (inverted) chip in bit 31; >>16 puts it on offset bit 15
-        A::mad(acc[j], lut_at_f<A>(lut, carrier_offset_bits(cph), (win << adv) & 0x80000000u, lane_off), g);
+        A::mad(acc[j], lut_at_f<A>(lut, carrier_index(cph), funnel_l(wlo, whi, adv), lane_off), g);
         x = dadd(x, d);
         cph = carrier_step_signed<kFalling>(cph, dc);
     }
@@ -626,10 +658,11 @@ GS_HD void synth_wrap_f(typename A::acc_t (&acc)[S], ChanStateF &st, const doubl
     typename A::gain_t g = A::make_gain(data_sign(nav_bits, st.bitk) * gain);
     const typename A::gain_t g_after = A::make_gain(data_sign(nav_bits, bit_after) * gain);
     uint32_t wrap_off = 0;
+    const uint32_t wlo = win << 9, whi = win >> 23;
 #pragma unroll
     for (int j = 0; j < S; j++) {
         const uint32_t adv = chips_since_signed(x, magic) + wrap_off;
-        A::mad(acc[j], lut_at_f<A>(lut, carrier_offset_bits(cph), (win << adv) & 0x80000000u, lane_off), g);
+        A::mad(acc[j], lut_at_f<A>(lut, carrier_index(cph), funnel_l(wlo, whi, adv), lane_off), g);
         x = dadd(x, d);
         cph = carrier_step_signed<kFalling>(cph, dc);
         const bool wrapped = x >= (double)kCaLen;

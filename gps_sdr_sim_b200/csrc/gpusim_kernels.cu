@@ -128,7 +128,16 @@ struct K2Smem {
     uint32_t *negw;         // inverted C/A chips, [33][35]
     uint32_t state;         // shared-window address of this thread's slot for channel 0
 };
-constexpr int kK2ThreadsFloat = 384; // FLOAT_CARR_PHASE kernel: 24 B of state per channel and thread
+#ifndef GS_FLOAT_S16
+#define GS_FLOAT_S16 1
+#endif
+#ifndef GS_K2_THREADS_FLOAT
+#define GS_K2_THREADS_FLOAT 384
+#endif
+// FLOAT_CARR_PHASE kernel: 24 B of state per channel and thread.  384 threads = 3 warps per SM
+// sub-partition, the most that can have more than 128 registers (the register file is per
+// sub-partition: 16384 / (4 warps x 32 lanes) = 128; 416 or 448 threads do not launch with 144).
+constexpr int kK2ThreadsFloat = GS_K2_THREADS_FLOAT;
 template <bool CF> struct K2Geom {
     static constexpr int kThreads = CF ? kK2ThreadsFloat : kK2Threads;
     static constexpr uint32_t kStride = (CF ? 24u : 16u) * kThreads; // bytes between channels
@@ -144,7 +153,7 @@ template <bool CF> struct K2Geom {
 // chain kernel disappears behind the synthesis kernel, which itself gets ~4 % slower.
 constexpr int k2_max_regs(bool carrier_float, bool shared_sm)
 {
-    return shared_sm ? 112 : (carrier_float ? 168 : 128);
+    return shared_sm ? 112 : (carrier_float ? ((65536 / kK2ThreadsFloat) > 255 ? 255 : (65536 / kK2ThreadsFloat) / 8 * 8) : 128);
 }
 
 size_t synth_smem_bytes_float(int max_active)
@@ -200,18 +209,23 @@ __device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows
     // that only other warps could hide, and there are just four warps per scheduler.  (Prefetching
     // more - carrier phase, chip words - measured slower: the kernel sits at the register limit.)
     uint4 r0n = make_uint4(0, 0, 0, 0); // d, steps, cthr | prn<<16 | gain8<<24
-    double xn = 0.0;
+    double xn = 0.0, dcn = 0.0; // (dcn: double carrier only - its load is a trip to L2 like the row's)
     if (live && nc > 0) {
         r0n = rows4[0];
         xn = lds_f64(sa);
+        if (CF)
+            dcn = dcs[0];
     }
     for (int k = 0; k < ncw; k++, sa += G::kStride) {
         const bool act = live && k < nc;
         const uint4 r0 = r0n;
         const double x = xn;
+        const double dc = dcn;
         if (live && k + 1 < nc) {
             r0n = rows4[2 * k + 2];
             xn = lds_f64(sa + G::kStride);
+            if (CF)
+                dcn = dcs[k + 1];
         }
         bool wrap = false;
         if (act)
@@ -241,7 +255,6 @@ __device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows
                 st.x = x;
                 st.cph = lds_f64(sa + G::kSecond);
                 const uint32_t meta = lds_u32(sa + G::kMeta);
-                const double dc = dcs[k];
                 // rising and falling carrier phase have their own loops (one wrap test each)
                 if (!any_wrap) {
                     if (dc < 0.0)
@@ -456,8 +469,11 @@ static cudaError_t launch_tuned_a(const DeviceJob &job, cudaStream_t stream)
 template <int FMT, int S>
 static cudaError_t launch_tuned(const DeviceJob &job, cudaStream_t stream)
 {
+    // Double carrier: always runs of 16 samples.  With 32 the compiler hoists the whole serial carrier
+    // chain of a run (32 x add/compare/select) in front of everything else, holds the 32 table indices
+    // in registers and spills the prefetched next-channel values - measured 6 % slower than S = 16.
     if (job.carrier_float)
-        return launch_tuned_a<AccF32x2, FMT, S, true>(job, stream);
+        return launch_tuned_a<AccF32x2, FMT, (GS_FLOAT_S16 ? 16 : S), true>(job, stream);
     if (S == 32 && job.accum == 1 && job.shared_sm)
         return launch_tuned_a<AccF32x2, FMT, 32, false, true>(job, stream);
     return job.accum == 1 ? launch_tuned_a<AccF32x2, FMT, S, false>(job, stream)

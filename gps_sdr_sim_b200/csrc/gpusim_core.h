@@ -26,6 +26,23 @@
 #define GS_HD inline
 #endif
 
+// Kernel-shape switches, each measured on B200 on the bench workload (tools/variant_bench.py):
+//   GS_ADDR_IMAD        table address = (phase >> 23) * 128 + replica base: the shift on the ALU pipe, the
+//                       multiply-add on the FMA pipe, instead of shift + LOP3 (both ALU).  4.303 -> 4.240 ms.
+//   GS_CHIP_GAIN_INT    integer carrier: the chip sign flips the sign bit of the fp32 gain (the broadcast operand
+//                       of FFMA2) instead of the top bit of the carrier phase.  No gain (4.315 ms): off.
+//   GS_CHIP_GAIN_FLOAT  double carrier: same; the table lookup then depends on the carrier chain only, one
+//                       instruction less on the kernel's critical path.  7.74 -> 7.16 ms: on.
+#ifndef GS_ADDR_IMAD
+#define GS_ADDR_IMAD 1
+#endif
+#ifndef GS_CHIP_GAIN_INT
+#define GS_CHIP_GAIN_INT 0
+#endif
+#ifndef GS_CHIP_GAIN_FLOAT
+#define GS_CHIP_GAIN_FLOAT 1
+#endif
+
 namespace gpusim {
 
 constexpr int kMaxChan = 16;
@@ -163,12 +180,15 @@ struct AccWide {
     typedef int32_t tab_t;
     typedef int32_t gain_t;
     static constexpr int kLaneMask = 31, kLaneShift = 2;
+    static constexpr bool kSignInGain = false; // an integer gain cannot be negated by flipping one bit
     static constexpr int kShiftQ = 4, kShiftI = 25;
     static constexpr int64_t kFieldBias = (1 << 20) + 64;
     static GS_HD acc_t init() { return (kFieldBias << kShiftI) + (kFieldBias << kShiftQ); }
     static GS_HD tab_t table_entry(int cosv, int sinv) { return cosv * (1 << 21) + sinv; }
     static GS_HD gain_t make_gain(int signed_gain) { return signed_gain * (1 << kShiftQ); }
     static GS_HD void mad(acc_t &acc, tab_t t, gain_t g) { acc = mad_wide(t, g, acc); }
+    static GS_HD void mad_s(acc_t &acc, tab_t t, uint32_t g) { acc = mad_wide(t, (gain_t)g, acc); } // unused (kSignInGain false)
+    static GS_HD uint32_t gain_bits(int signed_gain) { return (uint32_t)make_gain(signed_gain); }
     static GS_HD int32_t i_biased(acc_t acc) { return (int32_t)(acc >> 32); }
     static GS_HD int32_t q_biased(acc_t acc) { return (int32_t)(((uint32_t)acc >> 11) & 0x3fffu); }
 };
@@ -182,6 +202,7 @@ struct AccF32x2 {
     typedef uint64_t tab_t;
     typedef uint64_t gain_t;
     static constexpr int kLaneMask = 15, kLaneShift = 3;
+    static constexpr bool kSignInGain = true; // the chip sign can be the sign bit of the fp32 gain
     static constexpr uint32_t kMagicBits = 0x4b400000u; // 12582912.0f
     static GS_HD uint32_t fbits(float f)
     {
@@ -217,6 +238,16 @@ struct AccF32x2 {
         acc = pack(lo, hi);
 #endif
     }
+    // same with the gain as ONE fp32 value (bits gbits) for I and Q: the instruction's broadcast form
+    static GS_HD void mad_s(acc_t &acc, tab_t t, uint32_t gbits)
+    {
+#ifdef __CUDA_ARCH__
+        asm("{\n\t.reg .b64 gg;\n\tmov.b64 gg, {%2, %2};\n\tfma.rn.f32x2 %0, %1, gg, %0;\n\t}" : "+l"(acc) : "l"(t), "r"(gbits));
+#else
+        mad(acc, t, (uint64_t)gbits | ((uint64_t)gbits << 32));
+#endif
+    }
+    static GS_HD uint32_t gain_bits(int signed_gain) { return fbits((float)signed_gain); }
     // mantissa bits = sum + 64 (two's complement around the magic); +2^20 keeps the shift unsigned
     static GS_HD int32_t i_biased(acc_t acc) { return (int32_t)(((uint32_t)acc - kMagicBits + (1u << 20)) >> 7); }
     static GS_HD int32_t q_biased(acc_t acc) { return (int32_t)(((uint32_t)(acc >> 32) - kMagicBits + (1u << 20)) >> 7); }
@@ -449,8 +480,20 @@ GS_HD int data_sign(uint32_t nav_bits, int bitk) // +1 / -1, gpssim.c:2236
 template <class A>
 GS_HD typename A::tab_t lut_at(const typename A::tab_t *lut, uint32_t e, uint32_t lane_off)
 {
+#if defined(__CUDA_ARCH__) && GS_ADDR_IMAD
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(lut) + lane_off; // loop invariant
+    uint32_t addr;
+    asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(addr) : "r"(e >> 23), "r"(base));
+    typename A::tab_t v;
+    if (sizeof(typename A::tab_t) == 8)
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(*reinterpret_cast<uint64_t *>(&v)) : "r"(addr));
+    else
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(*reinterpret_cast<uint32_t *>(&v)) : "r"(addr));
+    return v;
+#else
     const uint32_t off = ((e >> 16) & 0xff80u) | lane_off; // (table index << 7) | replica, bytes
     return *reinterpret_cast<const typename A::tab_t *>(reinterpret_cast<const char *>(lut) + off);
+#endif
 }
 
 // the 32 (inverted) chips from chip c0 on, chip c0 in bit 31; the table continues past chip 1022
@@ -484,11 +527,15 @@ GS_HD void synth_fast(typename A::acc_t (&acc)[S], ChanState &st, const double d
     const int c0 = (int)x;
     const double magic = 4503599627370496.0 - (double)c0;
     const typename A::gain_t g = A::make_gain(signed_gain);
+    const uint32_t gb = A::gain_bits(signed_gain);
 #pragma unroll
     for (int j = 0; j < S; j++) {
         const uint32_t adv = chips_since(x, magic);
-        const uint32_t e = phs ^ ((win << adv) & 0x80000000u);
-        A::mad(acc[j], lut_at<A>(lut, e, lane_off), g);
+        const uint32_t chip = (win << adv) & 0x80000000u;
+        if (A::kSignInGain && GS_CHIP_GAIN_INT)
+            A::mad_s(acc[j], lut_at<A>(lut, phs, lane_off), gb ^ chip);
+        else
+            A::mad(acc[j], lut_at<A>(lut, phs ^ chip, lane_off), g);
         x = dadd(x, d);
         phs += steps;
     }
@@ -635,10 +682,14 @@ GS_HD void synth_fast_f(typename A::acc_t (&acc)[S], ChanStateF &st, const doubl
     // the window as a 64-bit value win << 9: shifted left by the chips advanced, bit 8 of the upper
     // word is the current chip (bit 31 - adv of win) - one funnel shift per sample
     const uint32_t wlo = win << 9, whi = win >> 23;
+    const uint32_t gb = A::gain_bits(signed_gain);
 #pragma unroll
     for (int j = 0; j < S; j++) {
         const uint32_t adv = chips_since(x, magic);
-        A::mad(acc[j], lut_at_f<A>(lut, carrier_index(cph), funnel_l(wlo, whi, adv), lane_off), g);
+        if (A::kSignInGain && GS_CHIP_GAIN_FLOAT) // chip sign on the gain: the lookup depends on the carrier phase only
+            A::mad_s(acc[j], lut_at_f<A>(lut, carrier_index(cph), 0u, lane_off), gb ^ ((win << adv) & 0x80000000u));
+        else
+            A::mad(acc[j], lut_at_f<A>(lut, carrier_index(cph), funnel_l(wlo, whi, adv), lane_off), g);
         x = dadd(x, d);
         cph = carrier_step_signed<kFalling>(cph, dc);
     }

@@ -6,7 +6,7 @@ import re
 import subprocess
 import sys
 
-LIB = "gps_sdr_sim_b200/libgpusim.so"
+LIB = __import__("os").environ.get("GPUSIM_LIB", "gps_sdr_sim_b200/libgpusim.so")
 
 
 def kernel_sass(pattern):

@@ -34,6 +34,12 @@ __global__ void __launch_bounds__(512, 1) probe(uint64_t *sink, double dseed, in
             if (MODE == 8) { w[i] = (int32_t)__umulhi((uint32_t)w[i], 0x10001u + it); }           // IMAD.HI
             if (MODE == 9) { a[i] = __dadd_rd(a[i], d); }                                        // DADD.RM
             if (MODE == 10) { asm volatile("prmt.b32 %0, %0, %1, 0x5432;" : "+r"(w[i]) : "r"(iseed)); } // PRMT
+            if (MODE == 11) { long long r; asm volatile("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(w[i]), "r"(it << 9), "l"((long long)gg)); w[i] = (int32_t)(r >> 32); } // IMAD.WIDE, high word used
+            if (MODE == 12) { a[i] = __fma_rn(a[i], d, dseed); }                                  // DFMA
+            if (MODE == 13) { w[i] = w[i] ^ (it & 0x80000000); }                                  // LOP3
+            if (MODE == 14) { w[i] = (uint32_t)w[i] >> 23; }                                        // SHF
+            if (MODE == 15) { w[i] = w[i] + iseed; }                                                // IADD
+            if (MODE == 16) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x78;" : "+r"(w[i]) : "r"(iseed), "r"(it)); w[i] = w[i] * 128 + iseed; } // LOP3 + IMAD pair (two pipes)
         }
     }
     uint64_t acc = 0;
@@ -75,5 +81,11 @@ int main()
     run<8>("IMAD.HI.U32", sink, sms);
     run<9>("DADD.RM", sink, sms);
     run<10>("PRMT", sink, sms);
+    run<11>("IMAD.WIDE (hi word)", sink, sms);
+    run<12>("DFMA", sink, sms);
+    run<13>("LOP3", sink, sms);
+    run<14>("SHF", sink, sms);
+    run<15>("IADD", sink, sms);
+    run<16>("LOP3+IMAD pair", sink, sms);
     return 0;
 }

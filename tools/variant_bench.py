@@ -1,0 +1,41 @@
+#!/usr/bin/env python3
+"""Time K2 of several builds of the library (tools/build_variant.py) on the bench shape and check that they
+all write the same bytes.  usage: python tools/variant_bench.py name[,name...] [epochs]
+Each build runs in its own process (the library is loaded once per process)."""
+import hashlib
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+if len(sys.argv) > 1 and sys.argv[1] == "--child":
+    sys.path.insert(0, ROOT)
+    import torch
+    import gps_sdr_sim_b200 as gs
+    E = int(sys.argv[2])
+    N = 260000
+    for mode, fmt in ((0, 8), (0, 16), (0, 1), (1, 8)):
+        t = gs.synthetic_table(E, N, 13, fmt, carrier_mode=mode)
+        out = torch.zeros(t.n_epochs * t.epoch_bytes, dtype=torch.uint8, device="cuda")
+        for pipeline in (0, 2) if mode == 0 and fmt == 8 else (0,):
+            with gs.GpuSim.for_table(t) as sim:
+                sim.set_option("pipeline", pipeline)
+                sim.upload_table(t)
+                best = 1e9
+                for _ in range(6):
+                    sim.generate_device(0, E, out.data_ptr(), out.numel())
+                    best = min(best, sim.timing().synth_ms)
+            torch.cuda.synchronize()
+            h = hashlib.sha256(out.cpu().numpy().tobytes()).hexdigest()[:16]
+            print(f"  mode={'FLOAT' if mode else 'INT'} fmt={fmt:2d} pipeline={pipeline} k2={best:7.3f} ms "
+                  f"{E * N / best / 1e6:7.1f} GS/s sha={h}", flush=True)
+    sys.exit(0)
+
+names = sys.argv[1].split(",")
+E = sys.argv[2] if len(sys.argv) > 2 else "2999"
+for n in names:
+    lib = os.path.join(ROOT, "variants", f"libgpusim_{n}.so")
+    print(f"== {n}", flush=True)
+    env = dict(os.environ, GPUSIM_LIB=lib)
+    subprocess.run([sys.executable, os.path.abspath(__file__), "--child", E], env=env, check=False)

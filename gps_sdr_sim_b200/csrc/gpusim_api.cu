@@ -71,7 +71,7 @@ struct gpusim_ctx {
     uint8_t *h_stage[2] = {nullptr, nullptr};
 
     // options
-    int opt_chunk = 0, opt_force_generic = 0, opt_force_slow = 0, opt_chain_replay = 0, opt_accum = 1, opt_layout = 0, opt_pipeline = 1;
+    int opt_chunk = 0, opt_force_generic = 0, opt_force_slow = 0, opt_chain_replay = 0, opt_accum = 1, opt_layout = 0, opt_pipeline = 1, opt_float_geom = 0;
     int opt_direct_first_mb = 16, opt_direct_mb = 64; // sub-batch sizes when copying straight into the caller's buffer
 
     gpusim_timing timing{};
@@ -197,6 +197,7 @@ SynthKernel plan_job(gpusim_ctx *ctx, int first, int n, uint8_t *out_dev, Device
     for (int e = first; e < first + n; e++)
         job.max_active = std::max<int>(job.max_active, ctx->h_nch[e]);
     job.force_wrap_path = ctx->opt_force_slow;
+    job.float_narrow = ctx->opt_float_geom == 1 ? 1 : 0;
 
     return which;
 }
@@ -478,6 +479,7 @@ int gpusim_set_option(gpusim_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "accum")) ctx->opt_accum = (int)value;
     else if (!strcmp(key, "layout")) ctx->opt_layout = (int)value;
     else if (!strcmp(key, "pipeline")) ctx->opt_pipeline = (int)value;
+    else if (!strcmp(key, "float_geom")) ctx->opt_float_geom = (int)value;
     else if (!strcmp(key, "direct_first_mb")) ctx->opt_direct_first_mb = (int)std::max<int64_t>(1, value);
     else if (!strcmp(key, "direct_mb")) ctx->opt_direct_mb = (int)std::max<int64_t>(1, value);
     else return fail(ctx, GPUSIM_ERR_ARG, "unknown option '%s'", key);

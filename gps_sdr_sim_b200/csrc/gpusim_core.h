@@ -42,6 +42,18 @@
 #ifndef GS_CHIP_GAIN_FLOAT
 #define GS_CHIP_GAIN_FLOAT 1
 #endif
+//   GS_PHASE_F64        integer carrier, fast loop: the 32-bit phase rides in the low mantissa word of a double
+//                       (1.5*2^52 + phase; adding the integer step is exact and the low word wraps mod 2^32 by
+//                       itself), so the per-sample phase add moves from the FMA pipe to the FP64 pipe.
+#ifndef GS_PHASE_F64
+#define GS_PHASE_F64 0
+#endif
+//   GS_PACK_FMA         16/8-bit output from the fp32 accumulators: (acc+64)>>7 (and >>4 more for 8-bit) taken by ONE
+//                       round-down FFMA2 per sample (I and Q) and the bytes gathered with PRMT - 2 / 2.5 instructions
+//                       per sample instead of 4 / 4.5 shifts and masks on the ALU pipe.
+#ifndef GS_PACK_FMA
+#define GS_PACK_FMA 1
+#endif
 
 namespace gpusim {
 
@@ -191,6 +203,8 @@ struct AccWide {
     static GS_HD uint32_t gain_bits(int signed_gain) { return (uint32_t)make_gain(signed_gain); }
     static GS_HD int32_t i_biased(acc_t acc) { return (int32_t)(acc >> 32); }
     static GS_HD int32_t q_biased(acc_t acc) { return (int32_t)(((uint32_t)acc >> 11) & 0x3fffu); }
+    static constexpr bool kFloorFma = false;
+    template <int K> static GS_HD uint64_t floor_shift(acc_t acc) { return (uint64_t)acc; } // unused
 };
 
 // (2) packed fp32x2 FMA (Blackwell FFMA2) on a float2 table entry (cos, sin).  All values are
@@ -251,6 +265,26 @@ struct AccF32x2 {
     // mantissa bits = sum + 64 (two's complement around the magic); +2^20 keeps the shift unsigned
     static GS_HD int32_t i_biased(acc_t acc) { return (int32_t)(((uint32_t)acc - kMagicBits + (1u << 20)) >> 7); }
     static GS_HD int32_t q_biased(acc_t acc) { return (int32_t)(((uint32_t)(acc >> 32) - kMagicBits + (1u << 20)) >> 7); }
+    // floor((sum + 64) / 2^K) for I (low half) and Q (high half), each as a two's complement number in the
+    // low mantissa bits of 1.5*2^23: acc * 2^-K + (1.5*2^23 - 1.5*2^23 * 2^-K), rounded down - the product
+    // is exact inside the FMA, and one unit of the result binade is 1.  K = 7 or 11.
+    static constexpr bool kFloorFma = GS_PACK_FMA != 0;
+    template <int K>
+    static GS_HD uint64_t floor_shift(acc_t acc)
+    {
+#ifdef __CUDA_ARCH__
+        const uint32_t sc = (uint32_t)(127 - K) << 23;                                   // 2^-K
+        const uint32_t m2 = __float_as_uint(12582912.0f - 12582912.0f / (float)(1 << K)); // exact: K <= 11
+        uint64_t r;
+        asm("{\n\t.reg .b64 ss, mm;\n\tmov.b64 ss, {%2, %2};\n\tmov.b64 mm, {%3, %3};\n\tfma.rm.f32x2 %0, %1, ss, mm;\n\t}"
+            : "=l"(r) : "l"(acc), "r"(sc), "r"(m2));
+        return r;
+#else
+        const uint32_t lo = kMagicBits + (uint32_t)((i_biased(acc) >> (K - 7)) - (8192 >> (K - 7)));
+        const uint32_t hi = kMagicBits + (uint32_t)((q_biased(acc) >> (K - 7)) - (8192 >> (K - 7)));
+        return (uint64_t)lo | ((uint64_t)hi << 32);
+#endif
+    }
 };
 
 // =====================================================================================
@@ -528,17 +562,30 @@ GS_HD void synth_fast(typename A::acc_t (&acc)[S], ChanState &st, const double d
     const double magic = 4503599627370496.0 - (double)c0;
     const typename A::gain_t g = A::make_gain(signed_gain);
     const uint32_t gb = A::gain_bits(signed_gain);
+#if defined(__CUDA_ARCH__) && GS_PHASE_F64
+    double pd = __hiloint2double(0x43380000, (int)phs); // 1.5 * 2^52 + phs
+    const double sd = (double)(int32_t)steps;           // any representative of steps mod 2^32 will do
+#endif
 #pragma unroll
     for (int j = 0; j < S; j++) {
         const uint32_t adv = chips_since(x, magic);
         const uint32_t chip = (win << adv) & 0x80000000u;
+#if defined(__CUDA_ARCH__) && GS_PHASE_F64
+        phs = (uint32_t)__double2loint(pd);
+        pd = __dadd_rn(pd, sd);
+#endif
         if (A::kSignInGain && GS_CHIP_GAIN_INT)
             A::mad_s(acc[j], lut_at<A>(lut, phs, lane_off), gb ^ chip);
         else
             A::mad(acc[j], lut_at<A>(lut, phs ^ chip, lane_off), g);
         x = dadd(x, d);
+#if !(defined(__CUDA_ARCH__) && GS_PHASE_F64)
         phs += steps;
+#endif
     }
+#if defined(__CUDA_ARCH__) && GS_PHASE_F64
+    phs = (uint32_t)__double2loint(pd);
+#endif
     st.x = x;
     st.phs = phs;
 }
@@ -755,9 +802,50 @@ GS_HD void store16(uint8_t *dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 #endif
 }
 
+GS_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) // PRMT: result byte i = byte (sel nibble i) of b:a
+{
+#ifdef __CUDA_ARCH__
+    return __byte_perm(a, b, sel);
+#else
+    const uint64_t v = (uint64_t)a | ((uint64_t)b << 32);
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++)
+        r |= (uint32_t)((v >> (8 * ((sel >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    return r;
+#endif
+}
+// one 16-bit sample (short I, short Q) / two 8-bit samples (I0 Q0 I1 Q1) from round-down FFMA2 results
+template <class A>
+GS_HD uint32_t word_sc16(typename A::acc_t acc)
+{
+    const uint64_t r = A::template floor_shift<7>(acc);
+    return byte_perm((uint32_t)r, (uint32_t)(r >> 32), 0x5410u);
+}
+template <class A>
+GS_HD uint32_t word_sc08(typename A::acc_t a0, typename A::acc_t a1)
+{
+    const uint64_t r0 = A::template floor_shift<11>(a0), r1 = A::template floor_shift<11>(a1);
+    return byte_perm(byte_perm((uint32_t)r0, (uint32_t)(r0 >> 32), 0x0040u),
+                     byte_perm((uint32_t)r1, (uint32_t)(r1 >> 32), 0x0040u), 0x5410u);
+}
+
 template <class A, int FMT, int S>
 GS_HD void store_run(uint8_t *dst, const typename A::acc_t (&acc)[S])
 {
+    if (A::kFloorFma && FMT == 16) {
+#pragma unroll
+        for (int q = 0; q < S / 4; q++)
+            store16(dst + 16 * q, word_sc16<A>(acc[4 * q]), word_sc16<A>(acc[4 * q + 1]), word_sc16<A>(acc[4 * q + 2]),
+                    word_sc16<A>(acc[4 * q + 3]));
+        return;
+    }
+    if (A::kFloorFma && FMT == 8) {
+#pragma unroll
+        for (int q = 0; q < S / 8; q++)
+            store16(dst + 16 * q, word_sc08<A>(acc[8 * q], acc[8 * q + 1]), word_sc08<A>(acc[8 * q + 2], acc[8 * q + 3]),
+                    word_sc08<A>(acc[8 * q + 4], acc[8 * q + 5]), word_sc08<A>(acc[8 * q + 6], acc[8 * q + 7]));
+        return;
+    }
 #define GS_P16(j) pack_sc16(A::i_biased(acc[j]), A::q_biased(acc[j]))
 #define GS_P08(j) pack_sc08(A::i_biased(acc[j]), A::q_biased(acc[j]))
 #define GS_P01(j) pack_sc01(A::i_biased(acc[j]), A::q_biased(acc[j]))

@@ -128,37 +128,39 @@ struct K2Smem {
     uint32_t *negw;         // inverted C/A chips, [33][35]
     uint32_t state;         // shared-window address of this thread's slot for channel 0
 };
-#ifndef GS_FLOAT_S16
-#define GS_FLOAT_S16 1
-#endif
+// FLOAT_CARR_PHASE kernel: 24 B of state per channel and thread.  Two geometries (CF = 1, 2):
+//   CF = 2  512 threads, 128 registers, runs of 32 samples - the fast one (6.2 ms on the bench shape), but the
+//           state of 512 threads only fits next to the tables for <= 13 active channels (227 KB per block);
+//   CF = 1  384 threads (3 warps per SM sub-partition, the most that can have more than 128 registers: the
+//           register file is per sub-partition, 16384 / (4 warps x 32 lanes) = 128), runs of 16 samples
+//           (7.2 ms) - tables with 14..16 active channels and the 16-sample kernel of low sample rates.
+// (Measured on B200: 384 threads with runs of 32: 8.3 ms; 512 threads with runs of 16: 9.1 ms, spills.)
 #ifndef GS_K2_THREADS_FLOAT
 #define GS_K2_THREADS_FLOAT 384
 #endif
-// FLOAT_CARR_PHASE kernel: 24 B of state per channel and thread.  384 threads = 3 warps per SM
-// sub-partition, the most that can have more than 128 registers (the register file is per
-// sub-partition: 16384 / (4 warps x 32 lanes) = 128; 416 or 448 threads do not launch with 144).
 constexpr int kK2ThreadsFloat = GS_K2_THREADS_FLOAT;
-template <bool CF> struct K2Geom {
-    static constexpr int kThreads = CF ? kK2ThreadsFloat : kK2Threads;
+constexpr int kFloatWideMaxChan = 13;
+template <int CF> struct K2Geom {
+    static constexpr int kThreads = CF == 1 ? kK2ThreadsFloat : kK2Threads;
     static constexpr uint32_t kStride = (CF ? 24u : 16u) * kThreads; // bytes between channels
     static constexpr uint32_t kSecond = 8u * kThreads;               // (phs, meta) / 512*carr_phase
     static constexpr uint32_t kMeta = CF ? 16u * kThreads : 8u * kThreads + 4u;
 };
 
 // Register cap of the synthesis kernel.  Normally one block owns the SM (launch bound: 128 registers
-// INT / 168 FLOAT at 512 / 384 threads).  The "shared SM" build of the INT kernel is capped at 112:
+// at 512 threads, 168 at 384).  The "shared SM" build of the INT kernel is capped at 112:
 // that leaves 2048 of the 16384 registers of every SM sub-partition free (4 warps x 32 lanes x 112 =
 // 14336), room for two warps of the NEXT call's chain kernel (k1_chain: 32-thread blocks, 32
 // registers) beside the resident block.  At 120 nothing fits (measured: no overlap); at 112 the
 // chain kernel disappears behind the synthesis kernel, which itself gets ~4 % slower.
-constexpr int k2_max_regs(bool carrier_float, bool shared_sm)
+constexpr int k2_max_regs(int cf, bool shared_sm)
 {
-    return shared_sm ? 112 : (carrier_float ? ((65536 / kK2ThreadsFloat) > 255 ? 255 : (65536 / kK2ThreadsFloat) / 8 * 8) : 128);
+    return shared_sm ? 112 : (cf == 1 ? ((65536 / kK2ThreadsFloat) > 255 ? 255 : (65536 / kK2ThreadsFloat) / 8 * 8) : 128);
 }
 
 size_t synth_smem_bytes_float(int max_active)
 {
-    return kSmemLut + kSmemNegw + (size_t)std::max(1, max_active) * K2Geom<true>::kStride;
+    return kSmemLut + kSmemNegw + (size_t)std::max(1, max_active) * (max_active <= kFloatWideMaxChan ? K2Geom<2>::kStride : K2Geom<1>::kStride);
 }
 
 __device__ __forceinline__ double lds_f64(uint32_t a)
@@ -191,7 +193,7 @@ __device__ __forceinline__ void sts_u32x2(uint32_t a, uint32_t v0, uint32_t v1)
 // the run; only then the (longer) wrap-aware loop is taken for that channel.
 // rows4: this epoch's rows as uint4 pairs; dcs: this epoch's carrier steps (double carrier only);
 // cthr_mask: 0xffff, or 0 to force the wrap-aware loop.
-template <class A, int FMT, int SR, bool CF>
+template <class A, int FMT, int SR, int CF>
 __device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows4, const double *dcs, const int nc,
                                           const int ncw, const bool live, const unsigned mask,
                                           const uint32_t lane_off, const uint32_t cthr_mask, uint8_t *dst)
@@ -280,7 +282,7 @@ __device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows
         store_run<A, FMT, SR>(dst, acc);
 }
 
-template <class A, int FMT, int S, bool CF, bool SHARED_SM>
+template <class A, int FMT, int S, int CF, bool SHARED_SM>
 __global__ void __maxnreg__(k2_max_regs(CF, SHARED_SM)) k2_synth(DeviceJob job)
 {
     typedef K2Geom<CF> G;
@@ -451,7 +453,7 @@ __global__ void __launch_bounds__(128) k2_generic(DeviceJob job)
     }
 }
 
-template <class A, int FMT, int S, bool CF, bool SHARED_SM = false>
+template <class A, int FMT, int S, int CF, bool SHARED_SM = false>
 static cudaError_t launch_tuned_a(const DeviceJob &job, cudaStream_t stream)
 {
     constexpr int T = K2Geom<CF>::kThreads;
@@ -469,15 +471,17 @@ static cudaError_t launch_tuned_a(const DeviceJob &job, cudaStream_t stream)
 template <int FMT, int S>
 static cudaError_t launch_tuned(const DeviceJob &job, cudaStream_t stream)
 {
-    // Double carrier: always runs of 16 samples.  With 32 the compiler hoists the whole serial carrier
-    // chain of a run (32 x add/compare/select) in front of everything else, holds the 32 table indices
-    // in registers and spills the prefetched next-channel values - measured 6 % slower than S = 16.
-    if (job.carrier_float)
-        return launch_tuned_a<AccF32x2, FMT, (GS_FLOAT_S16 ? 16 : S), true>(job, stream);
+    // Double carrier: 512 threads x runs of 32 samples when the per-thread state of all channels fits
+    // (<= 13 active channels), else 384 threads x runs of 16 (K2Geom).
+    if (job.carrier_float) {
+        if (S == 32 && job.max_active <= kFloatWideMaxChan && !job.float_narrow)
+            return launch_tuned_a<AccF32x2, FMT, 32, 2>(job, stream);
+        return launch_tuned_a<AccF32x2, FMT, 16, 1>(job, stream);
+    }
     if (S == 32 && job.accum == 1 && job.shared_sm)
-        return launch_tuned_a<AccF32x2, FMT, 32, false, true>(job, stream);
-    return job.accum == 1 ? launch_tuned_a<AccF32x2, FMT, S, false>(job, stream)
-                          : launch_tuned_a<AccWide, FMT, S, false>(job, stream);
+        return launch_tuned_a<AccF32x2, FMT, 32, 0, true>(job, stream);
+    return job.accum == 1 ? launch_tuned_a<AccF32x2, FMT, S, 0>(job, stream)
+                          : launch_tuned_a<AccWide, FMT, S, 0>(job, stream);
 }
 
 template <int FMT>

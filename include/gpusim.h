@@ -167,7 +167,9 @@ int gpusim_get_timing(const gpusim_ctx *ctx, gpusim_timing *out);
  *   "force_slow" 1 = always take the wrap-checking inner loop
  *   "direct_first_mb", "direct_mb" sub-batch sizes (MiB) of gpusim_generate_epochs (default 16, 64)
  *   "pipeline" 1 = (default) overlap the chain kernel with the previous call's synthesis kernel
- *              when the epoch is long enough for that to pay, 0 = never, 2 = whenever possible */
+ *              when the epoch is long enough for that to pay, 0 = never, 2 = whenever possible
+ *   "float_geom" FLOAT hosts: 0 = (default) 512-thread kernel when <= 13 channels are active, else the
+ *              384-thread one; 1 = always the 384-thread kernel */
 int gpusim_set_option(gpusim_ctx *ctx, const char *key, int64_t value);
 
 /*

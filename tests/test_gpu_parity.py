@@ -44,7 +44,8 @@ def test_cuda_reproduces_reference_bytes(name):
                                   "satellite_float_b16"])
 @pytest.mark.parametrize("opts", [{"force_slow": 1}, {"force_generic": 1}, {"chain_replay": 1}, {"accum": 0},
                                   {"layout": 1}, {"layout": 1, "chunk": 128}, {"layout": 1, "chunk": 2048},
-                                  {"layout": 1, "chunk": 96, "accum": 0}, {"layout": 1, "force_slow": 1}])
+                                  {"layout": 1, "chunk": 96, "accum": 0}, {"layout": 1, "force_slow": 1},
+                                  {"float_geom": 1}, {"float_geom": 1, "force_slow": 1}])
 def test_cuda_variants_agree(name, opts):
     table, want, _ = load_golden(name)
     table, want = table.slice(0, 5), want[:5]
@@ -227,3 +228,21 @@ def test_full_size_config2_properties():
     finally:
         for s in sims.values():
             s.close()
+
+
+@pytest.mark.parametrize("channels", [1, 13, 14, 16])
+@pytest.mark.parametrize("fmt", [gs.SC16, gs.SC01])
+def test_float_carrier_kernel_geometries(channels, fmt):
+    """FLOAT_CARR_PHASE hosts have two tuned kernels: 512 threads x runs of 32 samples while the
+    per-thread state of all channels fits in shared memory (<= 13 active channels), 384 threads x
+    runs of 16 beyond (and with float_geom=1).  Both against the oracle, and against each other."""
+    t = gs.synthetic_table(3, 260000, channels, fmt, seed=77 + channels, carrier_mode=gs.CARRIER_FLOAT)
+    want = oracle_lib.generate(t)
+    outs = []
+    for geom in (0, 1):
+        with gs.GpuSim.for_table(t) as sim:
+            sim.set_option("float_geom", geom)
+            outs.append(sim.generate_epochs(t))
+            assert sim.timing().fast_path == 1
+    assert np.array_equal(outs[0], want)
+    assert np.array_equal(outs[1], want)

@@ -70,7 +70,7 @@ def random_table():
     opts = {}
     if rng.random() < 0.5:
         opts = dict([(("force_slow", 1), ("layout", 1), ("accum", 0), ("chain_replay", 1), ("force_generic", 1),
-                      ("pipeline", 2), ("pipeline", 0))[int(rng.integers(7))]])
+                      ("pipeline", 2), ("pipeline", 0), ("float_geom", 1))[int(rng.integers(8))]])
         if "layout" in opts and rng.random() < 0.5:
             opts["chunk"] = int(rng.choice([64, 96, 128, 1024, 4096]))
     return t, opts, note

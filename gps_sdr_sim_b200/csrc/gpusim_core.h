@@ -205,6 +205,7 @@ struct AccWide {
     static GS_HD int32_t q_biased(acc_t acc) { return (int32_t)(((uint32_t)acc >> 11) & 0x3fffu); }
     static constexpr bool kFloorFma = false;
     template <int K> static GS_HD uint64_t floor_shift(acc_t acc) { return (uint64_t)acc; } // unused
+    static GS_HD uint64_t positive_signs(acc_t acc) { return (uint64_t)acc; }               // unused
 };
 
 // (2) packed fp32x2 FMA (Blackwell FFMA2) on a float2 table entry (cos, sin).  All values are
@@ -283,6 +284,19 @@ struct AccF32x2 {
         const uint32_t lo = kMagicBits + (uint32_t)((i_biased(acc) >> (K - 7)) - (8192 >> (K - 7)));
         const uint32_t hi = kMagicBits + (uint32_t)((q_biased(acc) >> (K - 7)) - (8192 >> (K - 7)));
         return (uint64_t)lo | ((uint64_t)hi << 32);
+#endif
+    }
+    // bit 31 of each half set iff the 16-bit sample (sum + 64) >> 7 is > 0, i.e. sum + 64 >= 128:
+    // (1.5*2^23 + 127) - acc is negative exactly then (an exact difference of integers; zero is +0).
+    static GS_HD uint64_t positive_signs(acc_t acc)
+    {
+#ifdef __CUDA_ARCH__
+        uint64_t r;
+        asm("{\n\t.reg .b64 ss, mm;\n\tmov.b64 ss, {%2, %2};\n\tmov.b64 mm, {%3, %3};\n\tfma.rn.f32x2 %0, %1, ss, mm;\n\t}"
+            : "=l"(r) : "l"(acc), "r"(0xbf800000u), "r"(__float_as_uint(12583039.0f)));
+        return r;
+#else
+        return (i_biased(acc) > 8192 ? 0x80000000ull : 0ull) | (q_biased(acc) > 8192 ? 0x80000000ull << 32 : 0ull);
 #endif
     }
 };
@@ -844,6 +858,29 @@ GS_HD void store_run(uint8_t *dst, const typename A::acc_t (&acc)[S])
         for (int q = 0; q < S / 8; q++)
             store16(dst + 16 * q, word_sc08<A>(acc[8 * q], acc[8 * q + 1]), word_sc08<A>(acc[8 * q + 2], acc[8 * q + 3]),
                     word_sc08<A>(acc[8 * q + 4], acc[8 * q + 5]), word_sc08<A>(acc[8 * q + 6], acc[8 * q + 7]));
+        return;
+    }
+    if (A::kFloorFma && FMT == 1) {
+        // byte b = samples 4b..4b+3 as I0 Q0 I1 Q1 I2 Q2 I3 Q3, MSB first (gpssim.c:2268-2274): one FFMA2 puts
+        // "I > 0" and "Q > 0" into two sign bits, one funnel shift each appends them to the byte
+#pragma unroll
+        for (int q = 0; q < S / 8; q++) {
+            uint32_t b[2] = {0u, 0u};
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint64_t r = A::positive_signs(acc[8 * q + 4 * h + j]);
+                    b[h] = funnel_l((uint32_t)r, b[h], 1u);
+                    b[h] = funnel_l((uint32_t)(r >> 32), b[h], 1u);
+                }
+            const uint16_t w = (uint16_t)byte_perm(b[0], b[1], 0x0040u);
+#ifdef __CUDA_ARCH__
+            *reinterpret_cast<uint16_t *>(dst + 2 * q) = w;
+#else
+            memcpy(dst + 2 * q, &w, 2);
+#endif
+        }
         return;
     }
 #define GS_P16(j) pack_sc16(A::i_biased(acc[j]), A::q_biased(acc[j]))

@@ -188,6 +188,11 @@ __device__ __forceinline__ void sts_u32x2(uint32_t a, uint32_t v0, uint32_t v1)
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v0), "r"(v1));
 }
 
+#ifndef GS_CHAN_UNROLL
+#define GS_CHAN_UNROLL 1
+#endif
+constexpr int kChanUnroll = GS_CHAN_UNROLL; // channel loop of synth_run
+
 // SR consecutive samples of one thread, all channels, packed and stored.
 // Lanes of a warp vote per channel on whether any of them may reach the 1023-chip wrap inside
 // the run; only then the (longer) wrap-aware loop is taken for that channel.
@@ -218,6 +223,7 @@ __device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows
         if (CF)
             dcn = dcs[0];
     }
+#pragma unroll kChanUnroll
     for (int k = 0; k < ncw; k++, sa += G::kStride) {
         const bool act = live && k < nc;
         const uint4 r0 = r0n;

@@ -126,6 +126,7 @@ template <class A>
 struct K2Smem {
     typename A::tab_t *lut; // replicated carrier table
     uint32_t *negw;         // inverted C/A chips, [33][35]
+    uint32_t negw_s;        // the same as a shared-window address (no generic-to-shared conversion per use)
     uint32_t state;         // shared-window address of this thread's slot for channel 0
 };
 // FLOAT_CARR_PHASE kernel: 24 B of state per channel and thread.  Two geometries (CF = 1, 2):
@@ -193,6 +194,13 @@ __device__ __forceinline__ void sts_u32x2(uint32_t a, uint32_t v0, uint32_t v1)
 #endif
 constexpr int kChanUnroll = GS_CHAN_UNROLL; // channel loop of synth_run
 
+// chip_window() through a 32-bit shared-window address: two LDS and one funnel shift
+__device__ __forceinline__ uint32_t chip_window_s(uint32_t negw_s, uint32_t prn, int c0)
+{
+    const uint32_t a = negw_s + (prn * (uint32_t)kCaWords + (uint32_t)(c0 >> 5)) * 4u;
+    return funnel_l(lds_u32(a + 4u), lds_u32(a), (uint32_t)c0 & 31u);
+}
+
 // SR consecutive samples of one thread, all channels, packed and stored.
 // Lanes of a warp vote per channel on whether any of them may reach the 1023-chip wrap inside
 // the run; only then the (longer) wrap-aware loop is taken for that channel.
@@ -235,13 +243,24 @@ __device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows
             if (CF)
                 dcn = dcs[k + 1];
         }
+        // The chip window (two LDS + funnel shift) and floor(x): the double-carrier kernel is latency bound and
+        // gains 3 % from ONE conversion shared by the wrap test and the window and from 32-bit shared
+        // addresses (6.17 -> 5.99 ms); the integer-carrier kernel is issue bound and LOSES 1.4 % with that
+        // shape (4.17 -> 4.23 ms: the window loads move in front of the branch on the vote), so it keeps the plain form.
+        int c0 = 0;
         bool wrap = false;
-        if (act)
+        if (CF) {
+            c0 = (int)x; // x = 0 on idle lanes
+            wrap = act && c0 >= (int)(r0.w & cthr_mask);
+        } else if (act) {
             wrap = (int)x >= (int)(r0.w & cthr_mask);
+        }
         const bool any_wrap = __any_sync(mask, wrap);
         if (act) {
             const double d = __hiloint2double((int)r0.y, (int)r0.x);
-            const uint32_t *nw = sm.negw + ((r0.w >> 16) & 0xffu) * kCaWords;
+            const uint32_t prn = (r0.w >> 16) & 0xffu;
+            const uint32_t win_f = CF ? chip_window_s(sm.negw_s, prn, c0) : 0u;
+            const uint32_t *nw = sm.negw + prn * kCaWords;
             if (!CF) {
                 ChanState st;
                 st.x = x;
@@ -266,17 +285,17 @@ __device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows
                 // rising and falling carrier phase have their own loops (one wrap test each)
                 if (!any_wrap) {
                     if (dc < 0.0)
-                        synth_fast_f<A, SR, true>(acc, st, d, dc, meta_sgain(meta), chip_window(nw, (int)x), sm.lut, lane_off);
+                        synth_fast_f<A, SR, true>(acc, st, d, dc, meta_sgain(meta), win_f, sm.lut, lane_off);
                     else
-                        synth_fast_f<A, SR, false>(acc, st, d, dc, meta_sgain(meta), chip_window(nw, (int)x), sm.lut, lane_off);
+                        synth_fast_f<A, SR, false>(acc, st, d, dc, meta_sgain(meta), win_f, sm.lut, lane_off);
                 } else {
                     const uint4 r1 = rows4[2 * k + 1];
                     st.icode = meta_icode(meta);
                     st.bitk = meta_bitk(meta);
                     if (dc < 0.0)
-                        synth_wrap_f<A, SR, true>(acc, st, d, dc, (int32_t)r1.y, r1.z, chip_window(nw, (int)x), sm.lut, lane_off);
+                        synth_wrap_f<A, SR, true>(acc, st, d, dc, (int32_t)r1.y, r1.z, win_f, sm.lut, lane_off);
                     else
-                        synth_wrap_f<A, SR, false>(acc, st, d, dc, (int32_t)r1.y, r1.z, chip_window(nw, (int)x), sm.lut, lane_off);
+                        synth_wrap_f<A, SR, false>(acc, st, d, dc, (int32_t)r1.y, r1.z, win_f, sm.lut, lane_off);
                     sts_u32(sa + G::kMeta, pack_meta(st.icode, st.bitk, data_sign(r1.z, st.bitk) * (int32_t)r1.y));
                 }
                 sts_f64(sa, st.x);
@@ -298,6 +317,7 @@ __global__ void __maxnreg__(k2_max_regs(CF, SHARED_SM)) k2_synth(DeviceJob job)
     K2Smem<A> sm;
     sm.lut = reinterpret_cast<tab_t *>(smem);
     sm.negw = reinterpret_cast<uint32_t *>(smem + kSmemLut);
+    sm.negw_s = (uint32_t)__cvta_generic_to_shared(sm.negw);
     uint32_t *lane_tab = sm.negw + kCaPrns * kCaWords;
 
     const int tid = threadIdx.x;

@@ -21,11 +21,11 @@ def val(k):
 rd,wr=val('dram__bytes_read.sum'),val('dram__bytes_write.sum')
 json.dump({"k2_synth_sc08_dram_bytes_per_launch": int(rd+wr), "dram_bytes_read": int(rd), "dram_bytes_write": int(wr),
            "algorithmic_bytes_per_launch": 2999*260000*2,
-           "source": "profiles/${R}_k2_synth_sc08_ncu.md (ncu --set full, one launch of k2_synth<AccF32x2,8,32,false,true>, 2999 epochs x 13 channels)"},
+           "source": "profiles/${R}_k2_synth_sc08_ncu.md (ncu --set full, one launch of k2_synth<AccF32x2,8,32,0,1>, 2999 epochs x 13 channels)"},
           open("$P/traffic.json","w"),indent=1)
 PY
 {
-echo "# $R — k2_synth<AccF32x2, 8, 32, false, true> (the 112-register build bench.py's back-to-back steps run): ncu --set full, one launch, bench workload"; echo
+echo "# $R — k2_synth<AccF32x2, 8, 32, 0, 1> (the 112-register build bench.py's back-to-back steps run): ncu --set full, one launch, bench workload"; echo
 echo "Command (B200, driver 580, CUDA 12.9): \`ncu --set full --clock-control none --import-source on -k regex:k2_synth -s 1 -c 1 python tools/profile_one.py 8 1 2999\`"
 echo "(2999 epochs x 13 channels x 260 000 samples, 8-bit IQ = the bench.py workload; the same command ran first without ncu.)"; echo
 python tools/ncu_summary.py $G/r01_k2_synth_sc08.ncu-rep; echo
@@ -36,10 +36,29 @@ echo "# $R — k1_chain<0>: ncu --set full, one launch, bench workload"; echo
 echo "\`ncu --set full --clock-control none --import-source on -k regex:k1_chain -s 1 -c 1 python tools/profile_one.py 8 1 2999\`"; echo
 python tools/ncu_summary.py $G/r01_k1_chain.ncu-rep
 } > $P/${R}_k1_chain_ncu.md
+if [ -f $G/k2_r01b.ncu-rep ]; then
+{
+echo "# $R — k2_synth<AccF32x2, 8, 32, 0, 0> (the 128-register build a single call runs): ncu --set full, one launch, bench workload"; echo
+echo "\`ncu --set full --clock-control none --import-source on -k regex:k2_synth -s 1 -c 1 python tools/profile_one.py 8 1 2999 0 0 0\`"; echo
+python tools/ncu_summary.py $G/k2_r01b.ncu-rep
+} > $P/${R}_k2_synth_sc08_128reg_ncu.md
+fi
+if [ -f $G/r01_k2_synth_float.ncu-rep ]; then
+{
+echo "# $R — k2_synth<AccF32x2, 8, 32, 2, false> (FLOAT_CARR_PHASE hosts: double carrier phase, 512 threads x runs of 32): ncu --set full, one launch, bench workload shape"; echo
+echo "\`ncu --set full --clock-control none --import-source on -k regex:k2_synth -s 1 -c 1 python tools/profile_one.py 8 1 2999 0 1 0\`"; echo
+python tools/ncu_summary.py $G/r01_k2_synth_float.ncu-rep
+} > $P/${R}_k2_synth_float_ncu.md
+fi
 {
 echo "# $R — launch list of \`python bench.py --steps 2 --warmup 3\` under ncu"; echo
 echo "\`ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv\` (cold-cache, serialised: shares, not absolutes). Raw list: ${R}_bench_launches.csv"; echo
-echo "Reading it next to the bench line: ncu runs one kernel at a time, so no call ever finds its predecessor in flight and the library takes its non-overlapped route (chain kernel, then the 128-register synthesis kernel \`<…, 0, 0>\`): K2 is 89 % of a serialised step.  In the un-profiled timed region the steps are issued back to back, the chain kernel of step i+1 runs beside the synthesis kernel of step i (112-register build \`<…, 0, 1>\`, profiled in ${R}_k2_synth_sc08_ncu.md) and the step is K2 alone: 4.46 ms of the 4.60 ms step = 97 % (bench.py \`kernels\`)."; echo
+python - <<PY
+import json
+b=json.load(open("$G/bench_r01.json"))
+k2=b["kernels"]["k2_synth_ms"]; st=b["ms_per_step"]
+print("Reading it next to the bench line: ncu runs one kernel at a time, so no call ever finds its predecessor in flight and the library takes its non-overlapped route (chain kernel, then the 128-register synthesis kernel \`<…, 0, 0>\`), and K2 is about nine tenths of a serialised step.  In the un-profiled timed region the steps are issued back to back, the chain kernel of step i+1 runs beside the synthesis kernel of step i (112-register build \`<…, 0, 1>\`, profiled in ${R}_k2_synth_sc08_ncu.md) and the step is K2 alone: %.2f ms of the %.2f ms step = %.0f %% (bench.py \`kernels\`).\n" % (k2, st, 100*k2/st))
+PY
 python - <<PY
 import csv, collections
 rows=[r for r in csv.reader(open('$G/r01_launches.csv')) if len(r)>5]

@@ -256,20 +256,33 @@ def main_b200(args):
         step()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k2_ms, k1_ms = [], []
+    k1_ms = []
     w0 = time.perf_counter()
     ev0.record(stream)
-    for _ in range(args.steps):
+    marks = [ev0]                                # one event between consecutive steps, on the launch stream
+    for i in range(args.steps):
         step()
+        if i + 1 < args.steps:
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record(stream)
     ev1.record(stream)
+    marks.append(ev1)
     barrier()
     w1 = time.perf_counter()
     clocks = sampler.window(w0, w1)
     ms = ev0.elapsed_time(ev1)
     # per-kernel durations of the last step (CUDA events recorded by the library on the same stream)
     t = sim.timing()
-    k2_ms.append(t.synth_ms)
     k1_ms.append(t.chain_ms)
+    k2_last_ms = t.synth_ms
+    # Average duration of the synthesis kernel's launches over the timed region.  With the chain kernel
+    # of the next step on the library's own stream, the launch stream carries nothing but the K2
+    # launches (they follow each other within 3 us, tools/step_gap.py), so the time between two marks
+    # is one K2 launch - including what the co-running chain kernel costs it, which the library's own
+    # event pair of the LAST step (no chain kernel beside it any more) does not show.  Without the
+    # overlap the chain kernel runs on the launch stream as well and is subtracted.
+    per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(len(marks) - 1)]
+    k2_ms = [m - (t.chain_ms if args.no_pipeline else 0.0) for m in per_step]
     launches_per_step = t.launches
     fast_path = t.fast_path
 
@@ -319,12 +332,13 @@ def main_b200(args):
                     "rank0_cpu_binding": numa,
                     "host_checksum": checksum},
             "gpu_launches": launches_per_step * args.steps,
-            "kernels": {"k1_chain_ms": sum(k1_ms) / len(k1_ms), "k2_synth_ms": k2, "tuned_kernel": bool(fast_path),
+            "kernels": {"k1_chain_ms": sum(k1_ms) / len(k1_ms), "k2_synth_ms": k2, "k2_synth_last_step_ms": k2_last_ms,
+                        "tuned_kernel": bool(fast_path),
                         "chain_overlaps_previous_synth": not args.no_pipeline},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "peak_source": peak_src,
                          "kernel": "k2_synth<8,32>", "algorithmic_bytes_per_launch": out_bytes,
-                         "note": "2 B/sample (SC08) x samples per launch / CUDA-event duration of the launch; "
+                         "note": "2 B/sample (SC08) x samples per launch / average CUDA-event duration of the K2 launches of the timed region; "
                                  "the kernel is instruction-issue bound (INT/FP64/LDS per sample and channel), see DESIGN.md"},
         }
         if world == 1:

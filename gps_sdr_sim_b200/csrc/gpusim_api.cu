@@ -238,9 +238,10 @@ int launch_range(gpusim_ctx *ctx, int first, int n, uint8_t *out_dev, cudaStream
     // Overlap pays when the synthesis kernel outlasts a chain kernel that is squeezed into the
     // registers K2 leaves free (there it runs ~4x slower than alone, and both scale with epochs x
     // channels, so the criterion is the epoch length): measured break-even near 200 000 samples per
-    // epoch.  FLOAT and the rarely used kernels have no shared-SM build - same stream for them.
+    // epoch.  FLOAT and the rarely used kernels have no shared-SM build (synth_has_shared_sm_build) - same
+    // stream for them.
     // And only when there is something to overlap with: the previous call's K2 is still in flight.
-    bool overlap = ctx->opt_pipeline != 0 && !job.carrier_float && which == SynthKernel::Tuned32 && job.accum == 1;
+    bool overlap = ctx->opt_pipeline != 0 && synth_has_shared_sm_build(job, which);
     if (overlap && ctx->opt_pipeline != 2) {
         overlap = job.n_samples >= kOverlapMinSamples && cudaEventQuery(ctx->ev_s1[slot ^ 1]) == cudaErrorNotReady;
         (void)cudaGetLastError(); // "not ready" is an answer, not an error

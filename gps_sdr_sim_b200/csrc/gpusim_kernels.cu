@@ -149,7 +149,7 @@ template <int CF> struct K2Geom {
 };
 
 // Register cap of the synthesis kernel.  Normally one block owns the SM (launch bound: 128 registers
-// at 512 threads, 168 at 384).  The "shared SM" build of the INT kernel is capped at 112:
+// at 512 threads, 168 at 384).  The "shared SM" builds of the 512-thread kernels are capped at 112:
 // that leaves 2048 of the 16384 registers of every SM sub-partition free (4 warps x 32 lanes x 112 =
 // 14336), room for two warps of the NEXT call's chain kernel (k1_chain: 32-thread blocks, 32
 // registers) beside the resident block.  At 120 nothing fits (measured: no overlap); at 112 the
@@ -521,6 +521,21 @@ static cudaError_t launch_generic(const DeviceJob &job, cudaStream_t stream)
     else
         k2_generic<FMT, false><<<blocks, threads, 0, stream>>>(job);
     return cudaGetLastError();
+}
+
+// Is there a build of the synthesis kernel for this job that leaves room for the next call's chain kernel?
+bool synth_has_shared_sm_build(const DeviceJob &job, SynthKernel which)
+{
+    if (which != SynthKernel::Tuned32)
+        return false;
+    // Double carrier: none.  Measured with a 112-register build of the 512-thread kernel (16 bytes of
+    // spills): its block fills the SM's shared memory (230 of 227 KiB - 1 KiB), so no chain block fits beside
+    // it at 13 channels, and where one does, the carrier chains - 3.7x the work of the code chains, and
+    // stretched ~3x when they share an SM - would outlast the synthesis kernel.  Serial 7.43 ms per step,
+    // "overlapped" 7.80 ms.
+    if (job.carrier_float)
+        return false;
+    return job.accum == 1;
 }
 
 cudaError_t launch_synth(const DeviceJob &job, SynthKernel which, cudaStream_t stream)

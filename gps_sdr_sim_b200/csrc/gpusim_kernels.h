@@ -52,6 +52,8 @@ enum class SynthKernel { Tuned32 = 0, Tuned16 = 1, Generic = 2 };
 cudaError_t launch_chain(const DeviceJob &job, ChainAlgo algo, cudaStream_t stream);
 // K2: samples -> bytes
 cudaError_t launch_synth(const DeviceJob &job, SynthKernel which, cudaStream_t stream);
+// true when launch_synth has a build for this job that can share the SM with the next call's chain kernel
+bool synth_has_shared_sm_build(const DeviceJob &job, SynthKernel which);
 // dynamic shared memory the tuned kernel needs for a given max_active (0 if it cannot run)
 size_t synth_smem_bytes(int max_active, int threads);
 int synth_threads();

@@ -57,7 +57,7 @@ python - <<PY
 import json
 b=json.load(open("$G/bench_r01.json"))
 k2=b["kernels"]["k2_synth_ms"]; st=b["ms_per_step"]
-print("Reading it next to the bench line: ncu runs one kernel at a time, so no call ever finds its predecessor in flight and the library takes its non-overlapped route (chain kernel, then the 128-register synthesis kernel \`<…, 0, 0>\`), and K2 is about nine tenths of a serialised step.  In the un-profiled timed region the steps are issued back to back, the chain kernel of step i+1 runs beside the synthesis kernel of step i (112-register build \`<…, 0, 1>\`, profiled in ${R}_k2_synth_sc08_ncu.md) and the step is K2 alone: %.2f ms of the %.2f ms step = %.0f %% (bench.py \`kernels\`).\n" % (k2, st, 100*k2/st))
+print("Reading it next to the bench line: ncu runs one kernel at a time, so no call ever finds its predecessor in flight and the library takes its non-overlapped route (chain kernel, then the 128-register synthesis kernel \`<…, 0, 0>\`), and K2 is about nine tenths of a serialised step.  In the un-profiled timed region the steps are issued back to back, the chain kernel of step i+1 runs beside the synthesis kernel of step i (112-register build \`<…, 0, 1>\`, profiled in ${R}_k2_synth_sc08_ncu.md) and the launch stream carries nothing but K2 launches: their average duration, %.2f ms, is %.0f %% of the %.2f ms step (bench.py \`kernels\`; the last step's K2, with no chain kernel beside it any more, takes %.2f ms).\n" % (k2, 100*k2/st, st, b["kernels"].get("k2_synth_last_step_ms", k2)))
 PY
 python - <<PY
 import csv, collections

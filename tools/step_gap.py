@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Back-to-back generate_device steps on the bench shape: ms per step next to the K2 duration, for a caller's
 stream of default and of high priority (is the gap between steps the chain kernel's blocks taking SM slots
-before the next synthesis kernel's blocks are placed?).  usage: python tools/step_gap.py [steps]"""
+before the next synthesis kernel's blocks are placed?).  usage: python tools/step_gap.py [steps] [carrier_mode]"""
 import os
 import sys
 
@@ -11,11 +11,12 @@ import torch
 import gps_sdr_sim_b200 as gs
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+mode = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # 0 integer carrier, 1 double carrier (FLOAT_CARR_PHASE hosts)
 E, N = 2999, 260000
-t = gs.synthetic_table(E, N, 13, 8)
+t = gs.synthetic_table(E, N, 13, 8, carrier_mode=mode)
 out = torch.empty(t.n_epochs * t.epoch_bytes, dtype=torch.uint8, device="cuda")
-for prio in (0, -1, 0, -1):
-    for pipeline in (1, 0):
+for prio in (0, -1):
+    for pipeline in (1, 0, 2):
         stream = torch.cuda.Stream(priority=prio)
         with gs.GpuSim.for_table(t) as sim:
             sim.set_option("pipeline", pipeline)

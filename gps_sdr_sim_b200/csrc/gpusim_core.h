@@ -42,12 +42,6 @@
 #ifndef GS_CHIP_GAIN_FLOAT
 #define GS_CHIP_GAIN_FLOAT 1
 #endif
-//   GS_PHASE_F64        integer carrier, fast loop: the 32-bit phase rides in the low mantissa word of a double
-//                       (1.5*2^52 + phase; adding the integer step is exact and the low word wraps mod 2^32 by
-//                       itself), so the per-sample phase add moves from the FMA pipe to the FP64 pipe.
-#ifndef GS_PHASE_F64
-#define GS_PHASE_F64 0
-#endif
 //   GS_PACK_FMA         16/8-bit output from the fp32 accumulators: (acc+64)>>7 (and >>4 more for 8-bit) taken by ONE
 //                       round-down FFMA2 per sample (I and Q) and the bytes gathered with PRMT - 2 / 2.5 instructions
 //                       per sample instead of 4 / 4.5 shifts and masks on the ALU pipe.
@@ -576,30 +570,17 @@ GS_HD void synth_fast(typename A::acc_t (&acc)[S], ChanState &st, const double d
     const double magic = 4503599627370496.0 - (double)c0;
     const typename A::gain_t g = A::make_gain(signed_gain);
     const uint32_t gb = A::gain_bits(signed_gain);
-#if defined(__CUDA_ARCH__) && GS_PHASE_F64
-    double pd = __hiloint2double(0x43380000, (int)phs); // 1.5 * 2^52 + phs
-    const double sd = (double)(int32_t)steps;           // any representative of steps mod 2^32 will do
-#endif
 #pragma unroll
     for (int j = 0; j < S; j++) {
         const uint32_t adv = chips_since(x, magic);
         const uint32_t chip = (win << adv) & 0x80000000u;
-#if defined(__CUDA_ARCH__) && GS_PHASE_F64
-        phs = (uint32_t)__double2loint(pd);
-        pd = __dadd_rn(pd, sd);
-#endif
         if (A::kSignInGain && GS_CHIP_GAIN_INT)
             A::mad_s(acc[j], lut_at<A>(lut, phs, lane_off), gb ^ chip);
         else
             A::mad(acc[j], lut_at<A>(lut, phs ^ chip, lane_off), g);
         x = dadd(x, d);
-#if !(defined(__CUDA_ARCH__) && GS_PHASE_F64)
         phs += steps;
-#endif
     }
-#if defined(__CUDA_ARCH__) && GS_PHASE_F64
-    phs = (uint32_t)__double2loint(pd);
-#endif
     st.x = x;
     st.phs = phs;
 }

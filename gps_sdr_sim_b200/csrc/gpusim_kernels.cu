@@ -189,11 +189,6 @@ __device__ __forceinline__ void sts_u32x2(uint32_t a, uint32_t v0, uint32_t v1)
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v0), "r"(v1));
 }
 
-#ifndef GS_CHAN_UNROLL
-#define GS_CHAN_UNROLL 1
-#endif
-constexpr int kChanUnroll = GS_CHAN_UNROLL; // channel loop of synth_run
-
 // chip_window() through a 32-bit shared-window address: two LDS and one funnel shift
 __device__ __forceinline__ uint32_t chip_window_s(uint32_t negw_s, uint32_t prn, int c0)
 {
@@ -231,7 +226,7 @@ __device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows
         if (CF)
             dcn = dcs[0];
     }
-#pragma unroll kChanUnroll
+#pragma unroll 1
     for (int k = 0; k < ncw; k++, sa += G::kStride) {
         const bool act = live && k < nc;
         const uint4 r0 = r0n;

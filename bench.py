@@ -180,14 +180,19 @@ def measured_peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the synthesis kernel from the committed ncu --set full capture."""
+def ncu_capture():
+    """figures of the committed ncu --set full capture of the synthesis kernel (profiles/traffic.json)"""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(p) as f:
-            return json.load(f).get("k2_synth_sc08_dram_bytes_per_launch")
+            return json.load(f)
     except Exception:  # noqa: BLE001
-        return None
+        return {}
+
+
+def ncu_traffic():
+    """dram bytes per launch of the synthesis kernel from the committed ncu --set full capture."""
+    return ncu_capture().get("k2_synth_sc08_dram_bytes_per_launch")
 
 
 def bind_to_gpu_cpus(index: int):
@@ -338,6 +343,10 @@ def main_b200(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "peak_source": peak_src,
                          "kernel": "k2_synth<8,32>", "algorithmic_bytes_per_launch": out_bytes,
+                         "issue": {"active_frac_ncu": (ncu_capture().get("issue_active_pct") or 0.0) / 100.0 or None,
+                                   "thread_instructions_per_sample_channel_ncu":
+                                       ncu_capture().get("thread_instructions_per_sample_channel"),
+                                   "source": "profiles/r01_k2_synth_sc08_ncu.md (not measured live)"},
                          "note": "2 B/sample (SC08) x samples per launch / average CUDA-event duration of the K2 launches of the timed region; "
                                  "the kernel is instruction-issue bound (INT/FP64/LDS per sample and channel), see DESIGN.md"},
         }

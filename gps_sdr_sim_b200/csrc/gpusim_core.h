@@ -345,11 +345,19 @@ GS_HD bool warp_any(unsigned mask, bool pred)
 //   carrier phase M = 512,  d = 512*RN(f_carr*delt), x = 512*carr_phase (FLOAT_CARR_PHASE hosts;
 //                 the power-of-two scaling commutes with every rounding)   gpssim.c:2245-2250
 // `mask`: the threads of the warp that walk chains together (device only).
-template <class Emit>
+// kSign: +1 the caller knows d >= 0 (the code phase), -1 d < 0, 0 decided at run time.  With a known
+// sign the test of the reference that can never fire and the other direction's jump are not compiled in
+// (a real step costs 17 instead of 31 instructions on the device, a jump trip ~20 fewer).
+#if defined(__GNUC__) || defined(__CUDACC__)
+#define GS_UNLIKELY(c) __builtin_expect(!!(c), 0)
+#else
+#define GS_UNLIKELY(c) (c)
+#endif
+template <int kSign = 0, class Emit>
 GS_HD double phase_chain(double x, const double d, const double M, const int n_end, const int every,
                          Emit emit, const unsigned mask = 0xffffffffu)
 {
-    const bool neg = d < 0.0;
+    const bool neg = kSign == 0 ? d < 0.0 : kSign < 0;
     const double ad = neg ? -d : d;
     const int ed = (int)((dbits(ad) >> 52) & 0x7ff) - 1023;
     const double rd = 1.0 / ad; // k = room/|delta| is estimated with 1/|d| and then corrected exactly
@@ -367,16 +375,16 @@ GS_HD double phase_chain(double x, const double d, const double M, const int n_e
     auto real_step = [&]() -> bool {
         x = dadd(x, d);
         bool wrapped = false;
-        if (x >= M) {
+        if (kSign >= 0 && x >= M) { // a rising chain leaves [0, M) at the top only, a falling one at the bottom
             x = dadd(x, -M);
             wrapped = true;
-        } else if (x < 0.0) {
+        } else if (kSign <= 0 && x < 0.0) {
             x = dadd(x, M);
             wrapped = true;
         }
         wraps += wrapped ? 1 : 0;
         n++;
-        if (n == next) {
+        if (GS_UNLIKELY(n == next)) {
             emit(j++, x, wraps);
             next += every;
         }
@@ -429,7 +437,7 @@ GS_HD double phase_chain(double x, const double d, const double M, const int n_e
                         k++;
                         y = dfma((double)k, delta, x);
                     }
-                    if (k > n_end - n) {
+                    if (GS_UNLIKELY(k > n_end - n)) {
                         k = n_end - n;
                         y = dfma((double)k, delta, x);
                     }
@@ -449,7 +457,7 @@ GS_HD double phase_chain(double x, const double d, const double M, const int n_e
                         k++;
                         y = dfma((double)k, delta, x);
                     }
-                    if (k > n_end - n) {
+                    if (GS_UNLIKELY(k > n_end - n)) {
                         k = n_end - n;
                         y = dfma((double)k, delta, x);
                     }
@@ -478,7 +486,7 @@ GS_HD void code_chain(double x, const double d, const int n_total, const int eve
                       const unsigned mask = 0xffffffffu)
 {
     const int last = ((n_total - 1) / every) * every; // sample index of the last checkpoint
-    phase_chain(x, d, (double)kCaLen, last, every, emit, mask);
+    phase_chain<1>(x, d, (double)kCaLen, last, every, emit, mask); // f_code*delt > 0
 }
 
 // Plain replay of the same chain (N dependent adds); kept as the in-tree cross-check of

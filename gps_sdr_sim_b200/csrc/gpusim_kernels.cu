@@ -53,7 +53,14 @@ __global__ void __maxnreg__(32) k1_chain(DeviceJob job)
                 x = carrier_step(x, job.dc[row]);
             }
         } else {
-            phase_chain(job.cph0[row], job.dc[row], kCarrMod, last, job.chunk, emit_c, mask);
+            // rising and falling chains have their own walk (one wrap test, one jump direction); the lanes of
+            // a warp are the same satellite in consecutive epochs and almost always agree on the sign
+            const double dc = job.dc[row];
+            const unsigned falling = __ballot_sync(mask, dc < 0.0);
+            if (dc < 0.0)
+                phase_chain<-1>(job.cph0[row], dc, kCarrMod, last, job.chunk, emit_c, falling);
+            else
+                phase_chain<1>(job.cph0[row], dc, kCarrMod, last, job.chunk, emit_c, mask & ~falling);
         }
         return;
     }

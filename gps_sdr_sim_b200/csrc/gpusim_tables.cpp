@@ -138,7 +138,9 @@ double gpusim_advance_carrier_f64(double carr_phase, double f_carr, double delt,
     if (n_samples <= 0 || d == 0.0)
         return carr_phase;
     auto nothing = [](int, double, int) {};
-    return gpusim::phase_chain(carr_phase * 512.0, (double)d * 512.0, 512.0, n_samples, 1 << 30, nothing) / 512.0;
+    const double x0 = carr_phase * 512.0, d512 = (double)d * 512.0;
+    return (d512 < 0.0 ? gpusim::phase_chain<-1>(x0, d512, 512.0, n_samples, 1 << 30, nothing)
+                       : gpusim::phase_chain<1>(x0, d512, 512.0, n_samples, 1 << 30, nothing)) / 512.0;
 }
 
 } // extern "C"

@@ -19,7 +19,10 @@ def val(k):
     x=float(v[h.index(k)]); un=u[h.index(k)]
     return x*{'Gbyte':1e9,'Mbyte':1e6,'Kbyte':1e3,'byte':1}.get(un,1)
 rd,wr=val('dram__bytes_read.sum'),val('dram__bytes_write.sum')
+issue=float(v[h.index('smsp__issue_active.avg.pct_of_peak_sustained_active')])
+inst=float(v[h.index('smsp__inst_executed.sum')])
 json.dump({"k2_synth_sc08_dram_bytes_per_launch": int(rd+wr), "dram_bytes_read": int(rd), "dram_bytes_write": int(wr),
+           "issue_active_pct": issue, "thread_instructions_per_sample_channel": inst*32/(2999*260000*13),
            "algorithmic_bytes_per_launch": 2999*260000*2,
            "source": "profiles/${R}_k2_synth_sc08_ncu.md (ncu --set full, one launch of k2_synth<AccF32x2,8,32,0,1>, 2999 epochs x 13 channels)"},
           open("$P/traffic.json","w"),indent=1)

@@ -227,6 +227,9 @@ def main_b200(args):
     torch.cuda.set_device(local_rank)
     numa = bind_to_gpu_cpus(local_rank)    # before any pinned allocation: keep staging memory NUMA-local
     if world > 1:
+        # stdout of rank 0 is ONE JSON line: NCCL_DEBUG=VERSION (set on some boxes) makes NCCL print its version there
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     # weak scaling: the job is `world` times longer in simulated time; rank r owns a contiguous

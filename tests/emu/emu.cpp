@@ -322,4 +322,15 @@ double emu_phase_chain(double x0, double d, double M, int n_end, int every, doub
     return phase_chain(x0, d, M, n_end, every, emit);
 }
 
+// the same walk through the compile-time-sign instantiations the device kernel and the host's
+// gpusim_advance_carrier_f64 use (phase_chain<1> for d >= 0, phase_chain<-1> for d < 0)
+double emu_phase_chain_signed(double x0, double d, double M, int n_end, int every, double *x_out, int *w_out)
+{
+    auto emit = [&](int j, double x, int wraps) {
+        x_out[j] = x;
+        w_out[j] = wraps;
+    };
+    return d < 0.0 ? phase_chain<-1>(x0, d, M, n_end, every, emit) : phase_chain<1>(x0, d, M, n_end, every, emit);
+}
+
 } // extern "C"

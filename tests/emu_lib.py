@@ -40,6 +40,8 @@ def lib() -> ctypes.CDLL:
         _lib.emu_phase_chain.restype = ctypes.c_double
         _lib.emu_phase_chain.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_void_p, ctypes.c_void_p]
+        _lib.emu_phase_chain_signed.restype = ctypes.c_double
+        _lib.emu_phase_chain_signed.argtypes = _lib.emu_phase_chain.argtypes
     return _lib
 
 
@@ -68,4 +70,9 @@ def phase_chain(x0: float, d: float, modulus: float, n_end: int, every: int):
     x = np.empty(k, dtype=np.float64)
     w = np.empty(k, dtype=np.int32)
     end = lib().emu_phase_chain(x0, d, modulus, n_end, every, x.ctypes.data, w.ctypes.data)
+    # the sign-specialised instantiations (what the device and the host advance use) must walk identically
+    xs, ws = np.empty_like(x), np.empty_like(w)
+    end_s = lib().emu_phase_chain_signed(x0, d, modulus, n_end, every, xs.ctypes.data, ws.ctypes.data)
+    assert np.array_equal(x.view(np.uint64), xs.view(np.uint64)) and np.array_equal(w, ws)
+    assert np.float64(end).view(np.uint64) == np.float64(end_s).view(np.uint64)
     return x, w, end

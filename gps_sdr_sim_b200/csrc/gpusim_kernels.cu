@@ -87,13 +87,13 @@ cudaError_t launch_chain(const DeviceJob &job, ChainAlgo algo, cudaStream_t stre
         return cudaSuccess;
     // Same shared-memory carve-out as the synthesis kernel: an SM cannot host two kernels that ask
     // for different L1/shared splits, and this kernel is meant to run beside the previous call's K2.
-    static const cudaError_t carve = []() {
-        cudaError_t e = cudaFuncSetAttribute(k1_chain<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(k1_chain<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-        return e;
-    }();
-    (void)carve;
+    // (Function attributes belong to the current device: set per launch, a host process may drive several GPUs.)
+    const cudaError_t carve =
+        algo == ChainAlgo::Replay
+            ? cudaFuncSetAttribute(k1_chain<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)
+            : cudaFuncSetAttribute(k1_chain<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (carve != cudaSuccess)
+        return carve;
     if (algo == ChainAlgo::Replay)
         k1_chain<true><<<blocks, threads, 0, stream>>>(job);
     else

@@ -59,12 +59,21 @@ constexpr int kCaWords = 35;         // per PRN, see gpusim_tables.h
 constexpr int kCaPrns = 33;          // index by prn 0..32 (0 unused)
 
 // ---- exact IEEE-754 double steps (never contracted into FMA) -----------------------
+// Host: the sum / product must be rounded to double on its own, never fused with a neighbouring
+// operation.  On x86-64 an empty asm that claims to modify the SSE register is such a barrier without
+// the store + load of a volatile (the host's carrier advance spends its time in these).
+#if !defined(__CUDA_ARCH__) && defined(__x86_64__) && defined(__GNUC__)
+#define GS_ROUND_HERE(r) __asm__ volatile("" : "+x"(r))
+#else
+#define GS_ROUND_HERE(r) do { volatile double gs_v_ = (r); (r) = gs_v_; } while (0)
+#endif
 GS_HD double dadd(double a, double b)
 {
 #ifdef __CUDA_ARCH__
     return __dadd_rn(a, b);
 #else
-    volatile double r = a + b;
+    double r = a + b;
+    GS_ROUND_HERE(r);
     return r;
 #endif
 }
@@ -73,7 +82,8 @@ GS_HD double dmul(double a, double b)
 #ifdef __CUDA_ARCH__
     return __dmul_rn(a, b);
 #else
-    volatile double r = a * b;
+    double r = a * b;
+    GS_ROUND_HERE(r);
     return r;
 #endif
 }

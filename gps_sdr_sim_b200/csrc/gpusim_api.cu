@@ -71,7 +71,7 @@ struct gpusim_ctx {
     uint8_t *h_stage[2] = {nullptr, nullptr};
 
     // options
-    int opt_chunk = 0, opt_force_generic = 0, opt_force_slow = 0, opt_chain_replay = 0, opt_accum = 1, opt_layout = 0, opt_pipeline = 1, opt_float_geom = 0;
+    int opt_chunk = 0, opt_force_generic = 0, opt_force_slow = 0, opt_chain_replay = 0, opt_accum = 1, opt_layout = 0, opt_pipeline = 1, opt_float_geom = 0, opt_lean = 1;
     int opt_direct_first_mb = 16, opt_direct_mb = 64; // sub-batch sizes when copying straight into the caller's buffer
 
     gpusim_timing timing{};
@@ -198,6 +198,7 @@ SynthKernel plan_job(gpusim_ctx *ctx, int first, int n, uint8_t *out_dev, Device
         job.max_active = std::max<int>(job.max_active, ctx->h_nch[e]);
     job.force_wrap_path = ctx->opt_force_slow;
     job.float_narrow = ctx->opt_float_geom == 1 ? 1 : 0;
+    job.lean = ctx->opt_lean;
 
     return which;
 }
@@ -481,6 +482,7 @@ int gpusim_set_option(gpusim_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "layout")) ctx->opt_layout = (int)value;
     else if (!strcmp(key, "pipeline")) ctx->opt_pipeline = (int)value;
     else if (!strcmp(key, "float_geom")) ctx->opt_float_geom = (int)value;
+    else if (!strcmp(key, "lean")) ctx->opt_lean = (int)value;
     else if (!strcmp(key, "direct_first_mb")) ctx->opt_direct_first_mb = (int)std::max<int64_t>(1, value);
     else if (!strcmp(key, "direct_mb")) ctx->opt_direct_mb = (int)std::max<int64_t>(1, value);
     else return fail(ctx, GPUSIM_ERR_ARG, "unknown option '%s'", key);
@@ -526,8 +528,8 @@ int gpusim_upload_table(gpusim_ctx *ctx, const gpusim_epoch_table *t)
             DevRow &o = ctx->h_rows[(size_t)e * kMaxChan + nc];
             o.d = d;
             o.steps = cf ? 0 : (int32_t)((uint32_t)t->carr_phasestep[r] << 7);
-            o.cthr = wrap_threshold(d);
-            o.prn = (uint8_t)t->prn[r];
+            o.cthr_prn = pack_cthr_prn(d, t->prn[r]);
+            o.woff = (uint16_t)(t->prn[r] * kCaWinBytes);
             o.ph0s = cf ? 0u : t->carr_phase[r] << 7;
             if (cf) {
                 // gpssim.c:2245: carr_phase += f_carr*delt (rounded product), phase in [0,1); kept x512
@@ -544,10 +546,7 @@ int gpusim_upload_table(gpusim_ctx *ctx, const gpusim_epoch_table *t)
             o.flags = 0;
             if (o.gain < 0 || o.gain > kTunedMaxGain) {
                 o.flags |= kRowNeedsGeneric;
-                o.gain8 = 0;
                 ctx->needs_generic = true;
-            } else {
-                o.gain8 = (uint8_t)o.gain;
             }
             ctx->d_max = std::max(ctx->d_max, (double)d);
             ctx->h_x0[(size_t)e * kMaxChan + nc] = x0;

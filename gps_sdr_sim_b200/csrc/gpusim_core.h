@@ -57,6 +57,9 @@ constexpr int kLutEntries = 512;
 constexpr int kLutBytes = 512 * 128;  // replicated carrier table: 512 entries, 128 bytes apart
 constexpr int kCaWords = 35;         // per PRN, see gpusim_tables.h
 constexpr int kCaPrns = 33;          // index by prn 0..32 (0 unused)
+constexpr int kCaWin64 = 34;         // per PRN: 64-bit windows {word i+1, word i}, i = 0..33 (one LDS.64 per chip window)
+constexpr int kCaWinBytes = kCaWin64 * 8;
+constexpr uint32_t kCthrMask = 0x3ffu;
 
 // ---- exact IEEE-754 double steps (never contracted into FMA) -----------------------
 // Host: the sum / product must be rounded to double on its own, never fused with a neighbouring
@@ -129,6 +132,31 @@ GS_HD uint32_t chips_since_signed(double x, double magic15)
     return (uint32_t)((int)x - c0);
 #endif
 }
+// floor(x) (0 <= x < 2^31) as an integer and the magic of chips_since() for it, 2^52 - floor(x), with two
+// FP64 adds and no conversion instruction: 2^52 + floor(x) = RD(x + 2^52), and 2^53 minus that is exact.
+GS_HD double floor_magic(double x, int &c0)
+{
+#ifdef __CUDA_ARCH__
+    const double m1 = __dadd_rd(x, 4503599627370496.0);
+    c0 = __double2loint(m1);
+    return __dadd_rn(9007199254740992.0, -m1);
+#else
+    c0 = (int)x;
+    return 4503599627370496.0 - (double)c0;
+#endif
+}
+// (hi:lo << (sh & 31)) >> 32: the hardware funnel shift takes the count modulo 32 by itself
+GS_HD uint32_t funnel_l_wrap(uint32_t lo, uint32_t hi, uint32_t sh)
+{
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm("shf.l.wrap.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(lo), "r"(hi), "r"(sh));
+    return r;
+#else
+    sh &= 31u;
+    return sh ? (hi << sh) | (lo >> (32 - sh)) : hi;
+#endif
+}
 GS_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t sh) // (hi:lo << sh) >> 32, sh in 0..31
 {
 #ifdef __CUDA_ARCH__
@@ -156,9 +184,8 @@ GS_HD int64_t mad_wide(int32_t a, int32_t b, int64_t c)
 struct alignas(16) DevRow {
     double d;          // RN(f_code*delt): the addend of gpssim.c:2212
     int32_t steps;     // carr_phasestep << 7 (gpssim.c:2176)
-    uint16_t cthr;     // a run starting at floor(code_phase) >= cthr may reach the 1023-chip wrap
-    uint8_t prn;
-    uint8_t gain8;     // gain[i] when it is 0..255 (tuned kernels)
+    uint16_t cthr_prn; // bits 0..9: a run starting at floor(code_phase) >= cthr may reach the 1023-chip wrap; bits 10..15: prn
+    uint16_t woff;     // byte offset of this PRN's chips in the kernel's 64-bit chip-window table (prn * kCaWinBytes)
     uint32_t ph0s;     // carr_phase at epoch start, << 7
     int32_t gain;      // gain[i], gpssim.c:2186
     uint32_t nav_bits; // next 32 data bits, MSB first
@@ -174,6 +201,9 @@ GS_HD uint16_t wrap_threshold(double d)
     const double t = 1022.0 - 33.0 * d;
     return t <= 0.0 ? (uint16_t)0 : (uint16_t)(int)t;
 }
+GS_HD uint16_t pack_cthr_prn(double d, int prn) { return (uint16_t)(wrap_threshold(d) | ((uint32_t)prn << 10)); }
+GS_HD int row_cthr(const DevRow &r) { return (int)(r.cthr_prn & kCthrMask); }
+GS_HD int row_prn(const DevRow &r) { return (int)(r.cthr_prn >> 10); }
 
 constexpr uint32_t kRowNeedsGeneric = 1u;
 constexpr int kTunedMaxGain = 255; // 16 ch * 250 * 255 + 64 < 2^20: the accumulator fields below hold it
@@ -602,6 +632,30 @@ GS_HD void synth_fast(typename A::acc_t (&acc)[S], ChanState &st, const double d
     st.x = x;
     st.phs = phs;
 }
+
+// The integer-carrier kernel's form of synth_fast: the signed gain arrives as fp32 bits (the broadcast
+// operand of FFMA2, kept in the thread's state so that no conversion is needed per run), the window
+// magic is computed by the caller together with floor(x) (floor_magic), sample 0 needs no chip advance,
+// and the low 7 bits of phs may carry the caller's bookkeeping (only bits 23..31 are ever looked at and
+// steps has its low 7 bits clear, gpssim.c:2202).
+template <class A, int S>
+GS_HD void synth_fast_g(typename A::acc_t (&acc)[S], double &x, uint32_t &phs, const double d, const uint32_t steps,
+                        const uint32_t gbits, const uint32_t win, const double magic, const typename A::tab_t *lut,
+                        const uint32_t lane_off)
+{
+#pragma unroll
+    for (int j = 0; j < S; j++) {
+        const uint32_t t = j == 0 ? win : win << chips_since(x, magic);
+        A::mad_s(acc[j], lut_at<A>(lut, phs ^ (t & 0x80000000u), lane_off), gbits);
+        x = dadd(x, d);
+        phs += steps;
+    }
+}
+
+// Per-thread, per-channel state of the integer-carrier kernel, 16 bytes in shared memory:
+//   x (f64) | carr_phase << 7, low 7 bits = icode0 + wraps so far in this epoch (<= 19 + 101) | fp32 bits of dataBit*gain
+GS_HD uint32_t lean_phase_word(uint32_t phs, int ic) { return (phs & ~127u) | (uint32_t)ic; }
+GS_HD int lean_ic(uint32_t phase_word) { return (int)(phase_word & 127u); }
 
 // Same samples, but the 1023-chip wrap (and with it the icode / data-bit walk of
 // gpssim.c:2214-2238) may happen inside the run - at most once, a run is far shorter than a

@@ -207,7 +207,7 @@ __device__ __forceinline__ uint32_t chip_window_s(uint32_t negw_s, uint32_t prn,
 // Lanes of a warp vote per channel on whether any of them may reach the 1023-chip wrap inside
 // the run; only then the (longer) wrap-aware loop is taken for that channel.
 // rows4: this epoch's rows as uint4 pairs; dcs: this epoch's carrier steps (double carrier only);
-// cthr_mask: 0xffff, or 0 to force the wrap-aware loop.
+// cthr_mask: kCthrMask, or 0 to force the wrap-aware loop.
 template <class A, int FMT, int SR, int CF>
 __device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows4, const double *dcs, const int nc,
                                           const int ncw, const bool live, const unsigned mask,
@@ -225,7 +225,7 @@ __device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows
     // early loads are safe).  Without it every channel begins with a load -> convert -> load chain
     // that only other warps could hide, and there are just four warps per scheduler.  (Prefetching
     // more - carrier phase, chip words - measured slower: the kernel sits at the register limit.)
-    uint4 r0n = make_uint4(0, 0, 0, 0); // d, steps, cthr | prn<<16 | gain8<<24
+    uint4 r0n = make_uint4(0, 0, 0, 0); // d, steps, cthr | prn<<10 | woff<<16
     double xn = 0.0, dcn = 0.0; // (dcn: double carrier only - its load is a trip to L2 like the row's)
     if (live && nc > 0) {
         r0n = rows4[0];
@@ -260,7 +260,7 @@ __device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows
         const bool any_wrap = __any_sync(mask, wrap);
         if (act) {
             const double d = __hiloint2double((int)r0.y, (int)r0.x);
-            const uint32_t prn = (r0.w >> 16) & 0xffu;
+            const uint32_t prn = (r0.w >> 10) & 63u;
             const uint32_t win_f = CF ? chip_window_s(sm.negw_s, prn, c0) : 0u;
             const uint32_t *nw = sm.negw + prn * kCaWords;
             if (!CF) {
@@ -343,7 +343,7 @@ __global__ void __maxnreg__(k2_max_regs(CF, SHARED_SM)) k2_synth(DeviceJob job)
     // value range and keeps (x & 0xff80) | lane_off as ONE LOP3
     const uint32_t lane_off = *reinterpret_cast<volatile uint32_t *>(lane_tab + (tid & 31));
     const int lane = tid & 31;
-    const uint32_t cthr_mask = job.force_wrap_path ? 0u : 0xffffu;
+    const uint32_t cthr_mask = job.force_wrap_path ? 0u : kCthrMask;
     constexpr int kBytesPer8 = (FMT == 16) ? 32 : (FMT == 8) ? 16 : 2;
 
     // Persistent warps: every warp repeatedly claims a unit of 32 chunks, one per lane.  No
@@ -425,6 +425,227 @@ __global__ void __maxnreg__(k2_max_regs(CF, SHARED_SM)) k2_synth(DeviceJob job)
 }
 
 // ------------------------------------------------------------------------------------
+// K2 integer carrier ("lean"): the same work decomposition and inner loop as k2_synth, with the
+// per-channel-per-run prologue cut down (42 instructions of overhead per 32 samples):
+//   * per-thread channel state is ONE 16-byte slot {x f64, carr_phase<<7 | icode0+wraps, fp32 bits of
+//     dataBit*gain}: one LDS.128 per run and channel, no unpacking or conversion of the gain;
+//   * the chip window is ONE LDS.64 from a table of overlapping 64-bit windows at a byte offset that
+//     comes ready-made in the row; the funnel shift takes its count modulo 32 by itself;
+//   * floor(x) and the window magic are two FP64 adds (floor_magic), no F2I / I2F;
+//   * sample 0 of a run needs no chip advance;
+//   * warps whose 32 lanes all work (same channel count, same run count - all but the last unit of
+//     an epoch group) run a loop without per-lane activity predicates.
+// shared memory: [carrier table 64 KB][chip windows 33*34*8][lane table][state 16 B x channels x threads]
+// ------------------------------------------------------------------------------------
+constexpr size_t kSmemWin64 = ((size_t)kCaPrns * kCaWinBytes + 32 * sizeof(uint32_t) + 15) & ~(size_t)15;
+constexpr uint32_t kLeanStride = 16u * (uint32_t)kK2Threads;
+#ifndef GS_LEAN_UNROLL
+#define GS_LEAN_UNROLL 1
+#endif
+#ifndef GS_LEAN_PF_STATE
+#define GS_LEAN_PF_STATE 1
+#endif
+constexpr bool kLeanPrefetchState = GS_LEAN_PF_STATE != 0; // also prefetch the next channel's state slot (the row always is)
+constexpr int kLeanUnroll = GS_LEAN_UNROLL; // channel-loop unroll factor (2 would drop the software pipeline's register moves)
+
+size_t lean_smem_bytes(int max_active) { return kSmemLut + kSmemWin64 + (size_t)std::max(1, max_active) * kLeanStride; }
+
+__device__ __forceinline__ uint4 lds_u32x4(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u32x4(uint32_t a, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v0), "r"(v1), "r"(v2), "r"(v3));
+}
+
+struct LeanSmem {
+    const uint64_t *lut; // replicated carrier table (float2 entries)
+    uint32_t win_s;      // shared-window address of the chip-window table
+    uint32_t state;      // shared-window address of this thread's slot for channel 0
+};
+
+template <int FMT, int SR, bool UNI>
+__device__ __forceinline__ void lean_run(const LeanSmem &sm, const uint4 *rows4, const int nc, const int ncw,
+                                         const bool live, const unsigned mask, const uint32_t lane_off,
+                                         const uint32_t cthr_mask, uint8_t *dst)
+{
+    typedef AccF32x2 A;
+    A::acc_t acc[SR];
+#pragma unroll
+    for (int j = 0; j < SR; j++)
+        acc[j] = A::init();
+
+    uint32_t sa = sm.state;
+    // software pipeline over channels: row and state of channel k+1 are in flight while channel k is generated
+    uint4 r0n = make_uint4(0, 0, 0, 0), stn = make_uint4(0, 0, 0, 0);
+    if (UNI || (live && nc > 0)) {
+        r0n = rows4[0];
+        if (kLeanPrefetchState)
+            stn = lds_u32x4(sa);
+    }
+#pragma unroll kLeanUnroll
+    for (int k = 0; k < ncw; k++, sa += kLeanStride) {
+        const bool act = UNI || (live && k < nc);
+        const uint4 r0 = r0n; // d, steps, cthr | prn<<10 | woff<<16
+        uint4 st = stn;       // x, phase word, gain bits
+        if (!kLeanPrefetchState && act)
+            st = lds_u32x4(sa);
+        if (UNI ? (k + 1 < ncw) : (live && k + 1 < nc)) {
+            r0n = rows4[2 * k + 2];
+            if (kLeanPrefetchState)
+                stn = lds_u32x4(sa + kLeanStride);
+        }
+        double x = __hiloint2double((int)st.y, (int)st.x);
+        int c0;
+        const double magic = floor_magic(x, c0); // idle lanes: x = 0
+        const bool wrap = act && c0 >= (int)(r0.w & cthr_mask);
+        const bool any_wrap = __any_sync(mask, wrap);
+        if (act) {
+            const double d = __hiloint2double((int)r0.y, (int)r0.x);
+            const uint2 ww = lds_u32x2(sm.win_s + (r0.w >> 16) + (((uint32_t)c0 >> 5) << 3)); // {word i+1, word i}
+            const uint32_t win = funnel_l_wrap(ww.x, ww.y, (uint32_t)c0);
+            uint32_t phs = st.z;
+            if (!any_wrap) {
+                synth_fast_g<A, SR>(acc, x, phs, d, r0.z, st.w, win, magic, sm.lut, lane_off);
+                sts_f64(sa, x);
+                sts_u32(sa + 8u, phs);
+            } else {
+                const uint4 r1 = rows4[2 * k + 1]; // ph0s, gain, nav_bits, icode0 | flags<<16
+                ChanState cs;
+                cs.x = x;
+                cs.phs = phs;
+                const int ic = lean_ic(phs);
+                cs.bitk = ic / 20;
+                cs.icode = ic - cs.bitk * 20;
+                synth_wrap<A, SR>(acc, cs, d, r0.z, (int32_t)r1.y, r1.z, win, sm.lut, lane_off);
+                const uint32_t gb = A::gain_bits(data_sign(r1.z, cs.bitk) * (int32_t)r1.y);
+                sts_u32x4(sa, (uint32_t)__double2loint(cs.x), (uint32_t)__double2hiint(cs.x),
+                          lean_phase_word(cs.phs, cs.bitk * 20 + cs.icode), gb);
+            }
+        }
+    }
+    if (live)
+        store_run<A, FMT, SR>(dst, acc);
+}
+
+template <int FMT, int S, bool SHARED_SM>
+__global__ void __maxnreg__(k2_max_regs(0, SHARED_SM)) k2_lean(DeviceJob job)
+{
+    typedef AccF32x2 A;
+    constexpr int T = kK2Threads;
+    extern __shared__ __align__(16) unsigned char smem[];
+    LeanSmem sm;
+    uint64_t *lut = reinterpret_cast<uint64_t *>(smem);
+    uint32_t *win = reinterpret_cast<uint32_t *>(smem + kSmemLut);
+    uint32_t *lane_tab = win + kCaPrns * kCaWin64 * 2;
+    sm.lut = lut;
+    sm.win_s = (uint32_t)__cvta_generic_to_shared(win);
+
+    const int tid = threadIdx.x;
+    sm.state = (uint32_t)__cvta_generic_to_shared(smem + kSmemLut + kSmemWin64) + (uint32_t)tid * 16u;
+    // replicated carrier table: entry i, replica r at byte i*128 + r*8 (a lane always reads its own replica)
+    for (int i = tid; i < kLutEntries * 16; i += T)
+        lut[i] = job.lut_f32[i >> 4];
+    // chip windows: entry (prn, i) = {inverted chips word i+1, word i}
+    for (int i = tid; i < kCaPrns * kCaWin64; i += T) {
+        const int prn = i / kCaWin64, w = i - prn * kCaWin64;
+        win[2 * i] = job.negw[prn * kCaWords + w + 1];
+        win[2 * i + 1] = job.negw[prn * kCaWords + w];
+    }
+    if (tid < 32)
+        lane_tab[tid] = (uint32_t)(tid & A::kLaneMask) << A::kLaneShift;
+    __syncthreads();
+
+    const uint32_t lane_off = *reinterpret_cast<volatile uint32_t *>(lane_tab + (tid & 31)); // opaque to ptxas (see k2_synth)
+    const int lane = tid & 31;
+    const uint32_t cthr_mask = job.force_wrap_path ? 0u : kCthrMask;
+    constexpr int kBytesPer8 = (FMT == 16) ? 32 : (FMT == 8) ? 16 : 2;
+
+    for (;;) {
+        unsigned int unit = 0;
+        if (lane == 0)
+            unit = atomicAdd(job.work_counter, 1u);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= (unsigned int)job.n_units)
+            break;
+        int e, jc;
+        bool valid;
+        if (job.ppe > 0) {
+            const unsigned int pg = unit / (unsigned int)job.q;
+            const unsigned int slot = unit - pg * (unsigned int)job.q;
+            const long long period = (long long)pg * 32 + lane;
+            valid = period < (long long)job.n_epochs * job.ppe;
+            e = (int)(period / job.ppe);
+            jc = (int)(period - (long long)e * job.ppe) * job.q + (int)slot;
+        } else {
+            const long long gid = (long long)unit * 32 + lane;
+            valid = gid < (long long)job.n_epochs * job.kc;
+            e = (int)(gid / job.kc);
+            jc = (int)(gid - (long long)e * job.kc);
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const int n0 = jc * job.chunk;
+            const int nrun = min(job.chunk, job.n_samples - n0);
+            const DevRow *rows = job.rows + (size_t)e * kMaxChan;
+            const uint4 *rows4 = reinterpret_cast<const uint4 *>(rows);
+            const int nc = job.nch[e];
+
+            // chunk-start state of every channel
+            uint32_t sa = sm.state;
+            for (int k = 0; k < nc; k++, sa += kLeanStride) {
+                const size_t ck = ((size_t)e * kMaxChan + k) * job.kc + jc;
+                const DevRow r = rows[k];
+                const int ic = (int)r.icode0 + (int)job.ck_w[ck];
+                const double x = job.ck_x[ck];
+                sts_u32x4(sa, (uint32_t)__double2loint(x), (uint32_t)__double2hiint(x),
+                          lean_phase_word(r.ph0s + (uint32_t)n0 * (uint32_t)r.steps, ic),
+                          A::gain_bits(data_sign(r.nav_bits, ic / 20) * r.gain));
+            }
+
+            const int ncw = (int)__reduce_max_sync(mask, (unsigned)nc);
+            const int full = nrun / S;
+            const int tail8 = (nrun - full * S) / 8;
+            const int full_w = (int)__reduce_max_sync(mask, (unsigned)full);
+            const int tail_w = (int)__reduce_max_sync(mask, (unsigned)tail8);
+            uint8_t *outp = job.out + (size_t)e * job.epoch_bytes + (size_t)(n0 / 8) * kBytesPer8;
+            // every lane works, on the same number of channels and runs: no activity predicates needed
+            const bool uni = mask == 0xffffffffu && __all_sync(mask, nc == ncw && full == full_w);
+
+            if (uni) {
+                for (int i = 0; i < full_w; i++)
+                    lean_run<FMT, S, true>(sm, rows4, nc, ncw, true, mask, lane_off, cthr_mask,
+                                           outp + (size_t)i * (S / 8) * kBytesPer8);
+            } else {
+                for (int i = 0; i < full_w; i++)
+                    lean_run<FMT, S, false>(sm, rows4, nc, ncw, i < full, mask, lane_off, cthr_mask,
+                                            outp + (size_t)i * (S / 8) * kBytesPer8);
+            }
+            for (int i = 0; i < tail_w; i++)
+                lean_run<FMT, 8, false>(sm, rows4, nc, ncw, i < tail8, mask, lane_off, cthr_mask,
+                                        outp + ((size_t)full * (S / 8) + i) * kBytesPer8);
+        }
+        __syncwarp();
+    }
+}
+
+template <int FMT, int S, bool SHARED_SM = false>
+static cudaError_t launch_lean(const DeviceJob &job, cudaStream_t stream)
+{
+    const size_t smem = lean_smem_bytes(job.max_active);
+    cudaError_t err = cudaFuncSetAttribute(k2_lean<FMT, S, SHARED_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess)
+        return err;
+    const long long warps_per_block = kK2Threads / 32;
+    const int blocks = (int)std::min<long long>(std::max(1, job.sm_count), ((long long)job.n_units + warps_per_block - 1) / warps_per_block);
+    k2_lean<FMT, S, SHARED_SM><<<blocks, kK2Threads, smem, stream>>>(job);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------
 // K2 generic
 // ------------------------------------------------------------------------------------
 template <int FMT, bool CF>
@@ -456,7 +677,7 @@ __global__ void __launch_bounds__(128) k2_generic(DeviceJob job)
         ch[k].icode = ic % 20;
         ch[k].bitk = ic / 20;
         ch[k].nav_bits = r.nav_bits;
-        ch[k].negw = job.negw + (size_t)r.prn * kCaWords;
+        ch[k].negw = job.negw + (size_t)row_prn(r) * kCaWords;
     }
 
     uint8_t *base = job.out + (size_t)e * job.epoch_bytes;
@@ -505,6 +726,11 @@ static cudaError_t launch_tuned(const DeviceJob &job, cudaStream_t stream)
         if (S == 32 && job.max_active <= kFloatWideMaxChan && !job.float_narrow)
             return launch_tuned_a<AccF32x2, FMT, 32, 2>(job, stream);
         return launch_tuned_a<AccF32x2, FMT, 16, 1>(job, stream);
+    }
+    if (job.accum == 1 && job.lean) {
+        if (S == 32 && job.shared_sm)
+            return launch_lean<FMT, 32, true>(job, stream);
+        return launch_lean<FMT, S>(job, stream);
     }
     if (S == 32 && job.accum == 1 && job.shared_sm)
         return launch_tuned_a<AccF32x2, FMT, 32, 0, true>(job, stream);

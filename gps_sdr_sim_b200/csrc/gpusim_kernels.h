@@ -42,6 +42,7 @@ struct DeviceJob {
     int32_t n_units;         // work units (32 chunks each) of the tuned kernel
     int32_t carrier_float;   // 1: FLOAT_CARR_PHASE host (double carrier phase), 0: integer carrier
     int32_t shared_sm;       // 1: K2 build that leaves registers for the next call's K1 (see k2_max_regs)
+    int32_t lean;            // 1: integer carrier runs k2_lean (default), 0: the round-1 k2_synth (kept as a cross-check)
     int32_t float_narrow;    // 1: FLOAT hosts always use the 384-thread build (test hook, see K2Geom)
 };
 

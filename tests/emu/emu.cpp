@@ -55,8 +55,8 @@ void emu_run(const Tables &T, const DevRow *rows, int nc, ChanState *st, uint32_
         acc[j] = A::init();
     for (int k = 0; k < nc; k++) {
         const DevRow &r = rows[k];
-        const bool wrap = (int)st[k].x >= (int)r.cthr || force_wrap;
-        const uint32_t *nw = T.negw.data() + (size_t)r.prn * kCaWords;
+        const bool wrap = (int)st[k].x >= row_cthr(r) || force_wrap;
+        const uint32_t *nw = T.negw.data() + (size_t)row_prn(r) * kCaWords;
         if (!wrap) {
             synth_fast<A, SR>(acc, st[k], r.d, (uint32_t)r.steps, meta_sgain(meta[k]), chip_window(nw, (int)st[k].x), lut, lane_off);
         } else {
@@ -94,6 +94,82 @@ void tuned_chunk(const Tables &T, const DevRow *rows, int nc, const double *ckx,
         emu_run<A, FMT, 8>(T, rows, nc, st, meta, force_wrap, lane_off, outp + ((size_t)full * (S / 8) + i) * kBytesPer8);
 }
 
+// ---- integer carrier, k2_lean (mirrors lean_run / k2_lean in gpusim_kernels.cu, one lane at a time) ----
+struct LeanSlot {
+    double x;
+    uint32_t phase_word, gain_bits;
+};
+template <int FMT, int SR>
+void emu_run_lean(const Tables &T, const std::vector<uint32_t> &win64, const DevRow *rows, int nc, LeanSlot *st,
+                  int force_wrap, uint32_t lane_off, uint8_t *dst)
+{
+    typedef AccF32x2 A;
+    const A::tab_t *lut = table_of<A>(T);
+    A::acc_t acc[SR];
+    for (int j = 0; j < SR; j++)
+        acc[j] = A::init();
+    for (int k = 0; k < nc; k++) {
+        const DevRow &r = rows[k];
+        double x = st[k].x;
+        int c0;
+        const double magic = floor_magic(x, c0);
+        const bool wrap = c0 >= row_cthr(r) || force_wrap;
+        const uint32_t *ww = win64.data() + (r.woff + (((uint32_t)c0 >> 5) << 3)) / 4; // {word i+1, word i}
+        const uint32_t win = funnel_l_wrap(ww[0], ww[1], (uint32_t)c0);
+        uint32_t phs = st[k].phase_word;
+        if (!wrap) {
+            synth_fast_g<A, SR>(acc, x, phs, r.d, (uint32_t)r.steps, st[k].gain_bits, win, magic, lut, lane_off);
+            st[k].x = x;
+            st[k].phase_word = phs;
+        } else {
+            ChanState cs;
+            cs.x = x;
+            cs.phs = phs;
+            const int ic = lean_ic(phs);
+            cs.bitk = ic / 20;
+            cs.icode = ic - cs.bitk * 20;
+            synth_wrap<A, SR>(acc, cs, r.d, (uint32_t)r.steps, r.gain, r.nav_bits, win, lut, lane_off);
+            st[k].x = cs.x;
+            st[k].phase_word = lean_phase_word(cs.phs, cs.bitk * 20 + cs.icode);
+            st[k].gain_bits = A::gain_bits(data_sign(r.nav_bits, cs.bitk) * r.gain);
+        }
+    }
+    store_run<A, FMT, SR>(dst, acc);
+}
+
+template <int FMT, int S>
+void tuned_chunk_lean(const Tables &T, const DevRow *rows, int nc, const double *ckx, const uint16_t *ckw, int kc,
+                      int jc, int chunk, int N, int force_wrap, int lane, uint8_t *epoch_out)
+{
+    typedef AccF32x2 A;
+    static std::vector<uint32_t> win64;
+    if (win64.empty()) {
+        win64.resize((size_t)kCaPrns * kCaWin64 * 2);
+        for (int i = 0; i < kCaPrns * kCaWin64; i++) {
+            const int prn = i / kCaWin64, w = i - prn * kCaWin64;
+            win64[2 * i] = T.negw[prn * kCaWords + w + 1];
+            win64[2 * i + 1] = T.negw[prn * kCaWords + w];
+        }
+    }
+    const int n0 = jc * chunk;
+    const int nrun = std::min(chunk, N - n0);
+    LeanSlot st[kMaxChan];
+    for (int k = 0; k < nc; k++) {
+        const int ic = rows[k].icode0 + ckw[k * kc + jc];
+        st[k].x = ckx[k * kc + jc];
+        st[k].phase_word = lean_phase_word(rows[k].ph0s + (uint32_t)n0 * (uint32_t)rows[k].steps, ic);
+        st[k].gain_bits = A::gain_bits(data_sign(rows[k].nav_bits, ic / 20) * rows[k].gain);
+    }
+    constexpr int kBytesPer8 = (FMT == 16) ? 32 : (FMT == 8) ? 16 : 2;
+    uint8_t *outp = epoch_out + (size_t)(n0 / 8) * kBytesPer8;
+    const uint32_t lane_off = (uint32_t)(lane & A::kLaneMask) << A::kLaneShift;
+    const int full = nrun / S, tail8 = (nrun - full * S) / 8;
+    for (int i = 0; i < full; i++)
+        emu_run_lean<FMT, S>(T, win64, rows, nc, st, force_wrap, lane_off, outp + (size_t)i * (S / 8) * kBytesPer8);
+    for (int i = 0; i < tail8; i++)
+        emu_run_lean<FMT, 8>(T, win64, rows, nc, st, force_wrap, lane_off, outp + ((size_t)full * (S / 8) + i) * kBytesPer8);
+}
+
 // ---- FLOAT_CARR_PHASE (double carrier phase) variants ---------------------------------------------
 template <class A, int FMT, int SR>
 void emu_run_f(const Tables &T, const DevRow *rows, const double *dcs, int nc, ChanStateF *st, uint32_t *meta,
@@ -105,8 +181,8 @@ void emu_run_f(const Tables &T, const DevRow *rows, const double *dcs, int nc, C
         acc[j] = A::init();
     for (int k = 0; k < nc; k++) {
         const DevRow &r = rows[k];
-        const bool wrap = (int)st[k].x >= (int)r.cthr || force_wrap;
-        const uint32_t *nw = T.negw.data() + (size_t)r.prn * kCaWords;
+        const bool wrap = (int)st[k].x >= row_cthr(r) || force_wrap;
+        const uint32_t *nw = T.negw.data() + (size_t)row_prn(r) * kCaWords;
         if (!wrap) {
             if (dcs[k] < 0.0)
                 synth_fast_f<A, SR, true>(acc, st[k], r.d, dcs[k], meta_sgain(meta[k]), chip_window(nw, (int)st[k].x), lut, lane_off);
@@ -173,7 +249,7 @@ void generic_chunk(const Tables &T, const DevRow *rows, const double *dcs, int n
         ch[k].icode = ic % 20;
         ch[k].bitk = ic / 20;
         ch[k].nav_bits = r.nav_bits;
-        ch[k].negw = T.negw.data() + (size_t)r.prn * kCaWords;
+        ch[k].negw = T.negw.data() + (size_t)row_prn(r) * kCaWords;
     }
     uint32_t byte = 0;
     for (int n = 0; n < nrun; n++) {
@@ -227,10 +303,9 @@ int emu_generate(const gpusim_epoch_table *t, int N, double delt, int fmt, int c
             DevRow &o = rows[nc];
             o.d = dmul(t->f_code[r], delt);
             o.steps = carrier_float ? 0 : (int32_t)((uint32_t)t->carr_phasestep[r] << 7);
-            o.cthr = wrap_threshold(o.d);
-            o.prn = (uint8_t)t->prn[r];
+            o.cthr_prn = pack_cthr_prn(o.d, t->prn[r]);
+            o.woff = (uint16_t)(t->prn[r] * kCaWinBytes);
             o.gain = t->gain[r];
-            o.gain8 = (uint8_t)o.gain;
             o.ph0s = carrier_float ? 0u : t->carr_phase[r] << 7;
             if (carrier_float) {
                 dcs[nc] = dmul(t->f_carr[r], delt) * 512.0;
@@ -276,7 +351,8 @@ int emu_generate(const gpusim_epoch_table *t, int N, double delt, int fmt, int c
 #define EMU_TUNED(F, S)                                                                                          \
     do {                                                                                                         \
         if (carrier_float) tuned_chunk_f<F, S>(T, rows, dcs, nc, ckx.data(), ckw.data(), ckc.data(), kc, jc, chunk, N, force_wrap, lane, eo); \
-        else if (accum == 1) tuned_chunk<AccF32x2, F, S>(T, rows, nc, ckx.data(), ckw.data(), kc, jc, chunk, N, force_wrap, lane, eo); \
+        else if (accum == 1) tuned_chunk_lean<F, S>(T, rows, nc, ckx.data(), ckw.data(), kc, jc, chunk, N, force_wrap, lane, eo); \
+        else if (accum == 3) tuned_chunk<AccF32x2, F, S>(T, rows, nc, ckx.data(), ckw.data(), kc, jc, chunk, N, force_wrap, lane, eo); \
         else tuned_chunk<AccWide, F, S>(T, rows, nc, ckx.data(), ckw.data(), kc, jc, chunk, N, force_wrap, lane, eo);            \
     } while (0)
 #define EMU_GENERIC(F)                                                                                           \

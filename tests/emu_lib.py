@@ -46,7 +46,9 @@ def lib() -> ctypes.CDLL:
 
 
 def generate(table, chunk: int = 512, kernel: int = TUNED32, force_wrap: bool = False,
-             chain_replay: bool = False, accum: int = 0) -> np.ndarray:
+             chain_replay: bool = False, accum: int = 1) -> np.ndarray:
+    """accum: 1 = what the product launches (k2_lean for integer carrier, k2_synth<AccF32x2> for double carrier),
+    3 = k2_synth<AccF32x2> for integer carrier (option lean=0), 0 = k2_synth<AccWide> (option accum=0)."""
     out = np.zeros(table.n_epochs * table.epoch_bytes, dtype=np.uint8)
     c = table.as_c()
     rc = lib().emu_generate(ctypes.addressof(c), table.samples_per_epoch, table.delt, table.data_format, chunk,

@@ -54,7 +54,8 @@ def test_device_algorithms_on_cpu_reproduce_reference_bytes(name):
 
 @pytest.mark.parametrize("name", ["static_int_b16", "static_int_b8", "static_int_b1", "satellite_int_b16",
                                   "static_float_b16", "satellite_float_b16", "circle_float_b8"])
-@pytest.mark.parametrize("variant", ["wrap_path", "generic", "tuned16", "replay_chain", "chunk128", "chunk2048"])
+@pytest.mark.parametrize("variant", ["wrap_path", "generic", "tuned16", "replay_chain", "chunk128", "chunk2048",
+                                     "acc_wide", "acc_wide_wrap", "round1_kernel", "round1_kernel_wrap"])
 def test_device_algorithm_variants_agree(name, variant):
     table, want, _ = load_golden(name)
     table, want = table.slice(0, 4), want[:4]
@@ -71,6 +72,12 @@ def test_device_algorithm_variants_agree(name, variant):
         kw["chunk"] = 128
     elif variant == "chunk2048":
         kw["chunk"] = 2048
+    elif variant.startswith("acc_wide"):
+        kw["accum"] = 0
+        kw["force_wrap"] = variant.endswith("wrap")
+    elif variant.startswith("round1_kernel"):
+        kw["accum"] = 3
+        kw["force_wrap"] = variant.endswith("wrap")
     out = emu_lib.generate(table, **kw)
     assert digests(out, table) == want
 

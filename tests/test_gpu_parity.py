@@ -45,7 +45,8 @@ def test_cuda_reproduces_reference_bytes(name):
 @pytest.mark.parametrize("opts", [{"force_slow": 1}, {"force_generic": 1}, {"chain_replay": 1}, {"accum": 0},
                                   {"layout": 1}, {"layout": 1, "chunk": 128}, {"layout": 1, "chunk": 2048},
                                   {"layout": 1, "chunk": 96, "accum": 0}, {"layout": 1, "force_slow": 1},
-                                  {"float_geom": 1}, {"float_geom": 1, "force_slow": 1}])
+                                  {"float_geom": 1}, {"float_geom": 1, "force_slow": 1},
+                                  {"lean": 0}, {"lean": 0, "force_slow": 1}, {"lean": 0, "layout": 1, "chunk": 128}])
 def test_cuda_variants_agree(name, opts):
     table, want, _ = load_golden(name)
     table, want = table.slice(0, 5), want[:5]

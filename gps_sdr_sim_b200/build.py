@@ -16,7 +16,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",   # Blackwell B200 only
     "-O3", "-lineinfo", "-std=c++17",
     "--fmad=false",                                 # never contract the reference's mul+add
-    "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-Wno-unknown-pragmas",
     "-Xptxas", "-v",
     "-cudart", "static",
     "-shared",

@@ -281,6 +281,7 @@ int drain(gpusim_ctx *ctx)
 {
     GS_CUDA(ctx, cudaStreamSynchronize(ctx->s_chain));
     GS_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
+    GS_CUDA(ctx, cudaStreamSynchronize(ctx->s_copy));
     for (int i = 0; i < 2; i++)
         GS_CUDA(ctx, cudaEventSynchronize(ctx->ev_s1[i]));
     return GPUSIM_OK;
@@ -581,8 +582,8 @@ int gpusim_generate_device(gpusim_ctx *ctx, int32_t first, int32_t n, void *out_
 {
     if (!ctx)
         return GPUSIM_ERR_ARG;
-    if (first < 0 || n < 0 || first + n > ctx->n_uploaded)
-        return fail(ctx, GPUSIM_ERR_ARG, "epoch range [%d,%d) outside the uploaded table (%d epochs)", first, first + n, ctx->n_uploaded);
+    if (first < 0 || n < 0 || first > ctx->n_uploaded || n > ctx->n_uploaded - first)
+        return fail(ctx, GPUSIM_ERR_ARG, "epoch range first=%d n=%d outside the uploaded table (%d epochs)", first, n, ctx->n_uploaded);
     if ((size_t)n * ctx->epoch_bytes > cap)
         return fail(ctx, GPUSIM_ERR_CAPACITY, "output needs %zu bytes, capacity is %zu", (size_t)n * ctx->epoch_bytes, cap);
     if (!out_device || ((uintptr_t)out_device & 15))
@@ -614,7 +615,28 @@ int gpusim_get_timing(const gpusim_ctx *cctx, gpusim_timing *out)
 
 // common driver of the two host-output entry points: sub-batches of <= kStageBytes are generated
 // on s_compute and copied back on s_copy while the next sub-batch is being generated
+static int generate_to_host_body(gpusim_ctx *ctx, const gpusim_epoch_table *t, uint8_t *out, gpusim_sink_fn sink, void *user);
+
+// Whatever way the body fails (CUDA error, sink failure), nothing of this call may still be running when
+// the caller gets the error back: kernels write the output buffer, copies write the staging buffers or
+// the caller's own memory.  Drain both streams; the slot's "synthesis done" event is recorded so that
+// later calls waiting on it see this call's work as finished.
 static int generate_to_host(gpusim_ctx *ctx, const gpusim_epoch_table *t, uint8_t *out, gpusim_sink_fn sink, void *user)
+{
+    const int rc = generate_to_host_body(ctx, t, out, sink, user);
+    if (rc != GPUSIM_OK && ctx->s_compute) {
+        const std::string keep = ctx->err;
+        cudaStreamSynchronize(ctx->s_compute);
+        cudaStreamSynchronize(ctx->s_copy);
+        cudaEventRecord(ctx->ev_s1[ctx->last_slot], ctx->s_compute);
+        cudaEventSynchronize(ctx->ev_s1[ctx->last_slot]);
+        (void)cudaGetLastError();
+        ctx->err = keep;
+    }
+    return rc;
+}
+
+static int generate_to_host_body(gpusim_ctx *ctx, const gpusim_epoch_table *t, uint8_t *out, gpusim_sink_fn sink, void *user)
 {
     int rc = gpusim_upload_table(ctx, t);
     if (rc != GPUSIM_OK)

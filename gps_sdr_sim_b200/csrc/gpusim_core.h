@@ -501,7 +501,14 @@ GS_HD double phase_chain(double x, const double d, const double M, const int n_e
                         k = n_end - n;
                         y = dfma((double)k, delta, x);
                     }
-                    ok = k > 0 && y >= c;
+                    // A landing exactly ON the edge 2^e is not a jump: below the edge the grid is twice as
+                    // fine, so the reference's sum may round to 2^e - ulp/2 where the coarse grid says 2^e.
+                    // Stop one step short; the step onto or over the edge is then a real addition.
+                    if (y == c) {
+                        k--;
+                        y = dfma((double)k, delta, x);
+                    }
+                    ok = k > 0 && y > c;
                 }
                 if (ok) {
                     // checkpoints that fall inside the jump

@@ -13,10 +13,30 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 
 #include "gpusim_kernels.h"
 
 namespace gpusim {
+
+// Function attributes belong to (device, kernel): set them the first time a kernel is launched on a
+// device, not on every launch.  One flag word per kernel instantiation, one bit per device.
+template <void (*K)(DeviceJob)>
+static cudaError_t set_attr_once(cudaFuncAttribute attr, int value)
+{
+    static std::atomic<unsigned long long> done{0ull};
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess)
+        return err;
+    const unsigned long long bit = dev < 64 ? 1ull << dev : 0ull;
+    if (bit && (done.load(std::memory_order_acquire) & bit))
+        return cudaSuccess;
+    err = cudaFuncSetAttribute(K, attr, value);
+    if (err == cudaSuccess && bit)
+        done.fetch_or(bit, std::memory_order_release);
+    return err;
+}
 
 // ------------------------------------------------------------------------------------
 // K1
@@ -87,11 +107,10 @@ cudaError_t launch_chain(const DeviceJob &job, ChainAlgo algo, cudaStream_t stre
         return cudaSuccess;
     // Same shared-memory carve-out as the synthesis kernel: an SM cannot host two kernels that ask
     // for different L1/shared splits, and this kernel is meant to run beside the previous call's K2.
-    // (Function attributes belong to the current device: set per launch, a host process may drive several GPUs.)
     const cudaError_t carve =
         algo == ChainAlgo::Replay
-            ? cudaFuncSetAttribute(k1_chain<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)
-            : cudaFuncSetAttribute(k1_chain<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+            ? set_attr_once<k1_chain<true>>(cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)
+            : set_attr_once<k1_chain<false>>(cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     if (carve != cudaSuccess)
         return carve;
     if (algo == ChainAlgo::Replay)
@@ -467,7 +486,7 @@ struct LeanSmem {
     uint32_t state;      // shared-window address of this thread's slot for channel 0
 };
 
-template <int FMT, int SR, bool UNI>
+template <int FMT, int SR, bool UNI, bool PF>
 __device__ __forceinline__ void lean_run(const LeanSmem &sm, const uint4 *rows4, const int nc, const int ncw,
                                          const bool live, const unsigned mask, const uint32_t lane_off,
                                          const uint32_t cthr_mask, uint8_t *dst)
@@ -483,7 +502,7 @@ __device__ __forceinline__ void lean_run(const LeanSmem &sm, const uint4 *rows4,
     uint4 r0n = make_uint4(0, 0, 0, 0), stn = make_uint4(0, 0, 0, 0);
     if (UNI || (live && nc > 0)) {
         r0n = rows4[0];
-        if (kLeanPrefetchState)
+        if (PF)
             stn = lds_u32x4(sa);
     }
 #pragma unroll kLeanUnroll
@@ -491,11 +510,11 @@ __device__ __forceinline__ void lean_run(const LeanSmem &sm, const uint4 *rows4,
         const bool act = UNI || (live && k < nc);
         const uint4 r0 = r0n; // d, steps, cthr | prn<<10 | woff<<16
         uint4 st = stn;       // x, phase word, gain bits
-        if (!kLeanPrefetchState && act)
+        if (!PF && act)
             st = lds_u32x4(sa);
         if (UNI ? (k + 1 < ncw) : (live && k + 1 < nc)) {
             r0n = rows4[2 * k + 2];
-            if (kLeanPrefetchState)
+            if (PF)
                 stn = lds_u32x4(sa + kLeanStride);
         }
         double x = __hiloint2double((int)st.y, (int)st.x);
@@ -563,6 +582,9 @@ __global__ void __maxnreg__(k2_max_regs(0, SHARED_SM)) k2_lean(DeviceJob job)
     const int lane = tid & 31;
     const uint32_t cthr_mask = job.force_wrap_path ? 0u : kCthrMask;
     constexpr int kBytesPer8 = (FMT == 16) ? 32 : (FMT == 8) ? 16 : 2;
+    // the next channel's state slot is prefetched too - except in the register-capped build, where the four
+    // extra live registers cost more than the load latency (measured: 4.61 -> 4.26 ms at 112 registers)
+    constexpr bool PF = kLeanPrefetchState && !SHARED_SM;
 
     for (;;) {
         unsigned int unit = 0;
@@ -617,15 +639,15 @@ __global__ void __maxnreg__(k2_max_regs(0, SHARED_SM)) k2_lean(DeviceJob job)
 
             if (uni) {
                 for (int i = 0; i < full_w; i++)
-                    lean_run<FMT, S, true>(sm, rows4, nc, ncw, true, mask, lane_off, cthr_mask,
+                    lean_run<FMT, S, true, PF>(sm, rows4, nc, ncw, true, mask, lane_off, cthr_mask,
                                            outp + (size_t)i * (S / 8) * kBytesPer8);
             } else {
                 for (int i = 0; i < full_w; i++)
-                    lean_run<FMT, S, false>(sm, rows4, nc, ncw, i < full, mask, lane_off, cthr_mask,
+                    lean_run<FMT, S, false, PF>(sm, rows4, nc, ncw, i < full, mask, lane_off, cthr_mask,
                                             outp + (size_t)i * (S / 8) * kBytesPer8);
             }
             for (int i = 0; i < tail_w; i++)
-                lean_run<FMT, 8, false>(sm, rows4, nc, ncw, i < tail8, mask, lane_off, cthr_mask,
+                lean_run<FMT, 8, false, PF>(sm, rows4, nc, ncw, i < tail8, mask, lane_off, cthr_mask,
                                         outp + ((size_t)full * (S / 8) + i) * kBytesPer8);
         }
         __syncwarp();
@@ -636,7 +658,7 @@ template <int FMT, int S, bool SHARED_SM = false>
 static cudaError_t launch_lean(const DeviceJob &job, cudaStream_t stream)
 {
     const size_t smem = lean_smem_bytes(job.max_active);
-    cudaError_t err = cudaFuncSetAttribute(k2_lean<FMT, S, SHARED_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = set_attr_once<k2_lean<FMT, S, SHARED_SM>>(cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lean_smem_bytes(kMaxChan));
     if (err != cudaSuccess)
         return err;
     const long long warps_per_block = kK2Threads / 32;
@@ -707,7 +729,9 @@ static cudaError_t launch_tuned_a(const DeviceJob &job, cudaStream_t stream)
 {
     constexpr int T = K2Geom<CF>::kThreads;
     const size_t smem = kSmemLut + kSmemNegw + (size_t)std::max(1, job.max_active) * K2Geom<CF>::kStride;
-    cudaError_t err = cudaFuncSetAttribute(k2_synth<A, FMT, S, CF, SHARED_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // the most this instantiation can ever ask for (CF = 2 only runs with <= kFloatWideMaxChan channels)
+    constexpr size_t smem_max = kSmemLut + kSmemNegw + (size_t)(CF == 2 ? kFloatWideMaxChan : kMaxChan) * K2Geom<CF>::kStride;
+    cudaError_t err = set_attr_once<k2_synth<A, FMT, S, CF, SHARED_SM>>(cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     if (err != cudaSuccess)
         return err;
     const long long units = job.n_units;

@@ -26,8 +26,12 @@ ROOT = os.path.dirname(HERE)
 REF = os.environ.get("GPSSIM_REFERENCE_DIR", "/root/reference")
 OUT = os.path.join(HERE, "_build")
 LIBDIR = os.path.join(ROOT, "gps_sdr_sim_b200")
-# the reference Makefile's flags (Makefile:8,12); no -march, no -ffast-math
-CFLAGS = ["-O3", "-Wall", "-D_FILE_OFFSET_BITS=64"]
+# the reference Makefile's flags (Makefile:8,12); no -march, no -ffast-math.  -ffp-contract=off states what
+# those flags mean on x86-64 (no FMA without -march): libgpusim reproduces "code_phase += f_code*delt" and
+# "carr_phase += f_carr*delt" as a rounded product followed by a rounded sum (gpssim.c:2212, :2245).  On a
+# target whose baseline has FMA (aarch64) GCC's default -ffp-contract=fast would fuse them and change
+# the bytes of the reference itself; the binding is defined against the unfused arithmetic.
+CFLAGS = ["-O3", "-Wall", "-D_FILE_OFFSET_BITS=64", "-ffp-contract=off"]
 
 
 def apply_binding(src: str) -> str:

@@ -14,8 +14,8 @@
  *                        memory-derived cap of at most 4096)
  *   GPUSIM_DEVICE        CUDA device ordinal                (default 0)
  *   GPUSIM_DEVICES       number of GPUs (devices 0..n-1) to time-shard batches over (default 1):
- *                        batch b goes to device b mod n; one worker thread per GPU generates into
- *                        page-locked buffers, one writer thread fwrites the batches in order
+ *                        whichever GPU is free takes the next batch; one worker thread per GPU generates
+ *                        into page-locked buffers, one writer thread fwrites the batches in order
  *   GPUSIM_DEVICE_LIST   same, with explicit ordinals, e.g. "0,2,5" (or "0,0" to run two workers
  *                        on one GPU)
  *   GPUSIM_DUMP          path: also write every table row to this file
@@ -133,8 +133,9 @@ typedef struct
 {
 	struct gpusim_hook *h;
 	gpusim_ctx *ctx;
-	int index; /* worker d serves batches d, d+n, d+2n, ... */
+	int index;
 	int device;
+	long batches; /* batches this worker generated (GPUSIM_VERBOSE) */
 	pthread_t thread;
 } worker_t;
 
@@ -165,7 +166,11 @@ struct gpusim_hook
 	pthread_mutex_t mu;
 	pthread_cond_t cv;
 	long seq_filled; /* batches handed to the workers so far */
+	long seq_taken;  /* batches claimed by a worker so far: whichever GPU is free takes the next one */
 	int finishing;   /* no more batches will be queued */
+	int failed;      /* a worker or the writer hit an error: everybody stops, the MAIN thread reports and exits */
+	char fail_msg[600];
+	long epochs_written; /* epochs delivered to the output file so far (what a failure report states) */
 };
 
 static double now_s(void)
@@ -180,6 +185,13 @@ static void die(const char *what, const char *detail)
 	fprintf(stderr, "\nERROR: %s%s%s\n", what, detail ? ": " : "", detail ? detail : "");
 	exit(1);
 }
+
+/* A failure on a worker or writer thread: record it and wake everybody.  Nothing exits from those
+ * threads - another thread may be in the middle of an fwrite.  The main thread notices at its next
+ * hand-over (or at close), joins the pipeline, flushes what was written and exits like the reference
+ * does (message on stderr, status 1). */
+static void pipeline_fail(struct gpusim_hook *h, const char *what, const char *detail);
+static void pipeline_check(struct gpusim_hook *h);
 
 static void *xrealloc(void *p, size_t n)
 {
@@ -467,24 +479,71 @@ void gpusim_hook_range(gpusim_hook *h, range_t *rho, int slot, int iumd, int num
 }
 
 /* ---- GPU pipeline: workers generate, batches are written strictly in order --------------------- */
+static void pipeline_fail(gpusim_hook *h, const char *what, const char *detail)
+{
+	pthread_mutex_lock(&h->mu);
+	if (!h->failed)
+	{
+		h->failed = 1;
+		snprintf(h->fail_msg, sizeof(h->fail_msg), "%s%s%s", what, detail ? ": " : "", detail ? detail : "");
+	}
+	pthread_cond_broadcast(&h->cv);
+	pthread_mutex_unlock(&h->mu);
+}
+
+static void pipeline_join(gpusim_hook *h)
+{
+	int d;
+	pthread_mutex_lock(&h->mu);
+	h->finishing = 1;
+	pthread_cond_broadcast(&h->cv);
+	pthread_mutex_unlock(&h->mu);
+	for (d = 0; d < h->ndev; d++)
+		pthread_join(h->workers[d].thread, NULL);
+	if (h->ndev > 1)
+		pthread_join(h->writer, NULL);
+}
+
+/* main thread only */
+static void pipeline_check(gpusim_hook *h)
+{
+	int failed;
+	if (h->dryrun)
+		return;
+	pthread_mutex_lock(&h->mu);
+	failed = h->failed;
+	pthread_mutex_unlock(&h->mu);
+	if (!failed)
+		return;
+	pipeline_join(h);
+	fflush(h->fp);
+	fprintf(stderr, "\nERROR: %s\n       (%ld of the epochs handed over so far were written to the output before the failure)\n",
+	        h->fail_msg, h->epochs_written);
+	exit(1);
+}
+
 static void *worker_main(void *arg)
 {
 	worker_t *w = (worker_t *)arg;
 	gpusim_hook *h = w->h;
-	long seq;
-	for (seq = w->index;; seq += h->ndev)
+	for (;;)
 	{
-		slot_t *s = &h->slots[seq % h->nslots];
+		slot_t *s;
 		gpusim_epoch_table t;
+		long seq;
 		int rc;
+		/* Whichever GPU is free takes the next batch (not batch b -> GPU b mod n): the GPUs of a box do
+		 * not share the host link evenly, and an even split would let the slowest link set the pace. */
 		pthread_mutex_lock(&h->mu);
-		while (!(s->state == SLOT_QUEUED && seq < h->seq_filled) && !(h->finishing && seq >= h->seq_filled))
+		while (!h->failed && h->seq_taken >= h->seq_filled && !h->finishing)
 			pthread_cond_wait(&h->cv, &h->mu);
-		if (seq >= h->seq_filled)
+		if (h->failed || h->seq_taken >= h->seq_filled)
 		{
 			pthread_mutex_unlock(&h->mu);
 			return NULL;
 		}
+		seq = h->seq_taken++;
+		s = &h->slots[seq % h->nslots];
 		pthread_mutex_unlock(&h->mu);
 
 		table_of(&s->rows, &t);
@@ -493,9 +552,16 @@ static void *worker_main(void *arg)
 		else
 			rc = gpusim_generate_epochs(w->ctx, &t, s->out, (size_t)h->cap_max * gpusim_epoch_bytes(w->ctx));
 		if (rc != GPUSIM_OK)
-			die("GPU sample generation failed", gpusim_last_error(w->ctx));
+		{
+			pipeline_fail(h, rc == GPUSIM_ERR_SINK ? "Failed to write the output file" : "GPU sample generation failed",
+			              gpusim_last_error(w->ctx));
+			return NULL;
+		}
+		w->batches++;
 
 		pthread_mutex_lock(&h->mu);
+		if (h->ndev == 1)
+			h->epochs_written += s->rows.n;
 		s->state = h->ndev == 1 ? SLOT_FREE : SLOT_DONE;
 		pthread_cond_broadcast(&h->cv);
 		pthread_mutex_unlock(&h->mu);
@@ -511,9 +577,9 @@ static void *writer_main(void *arg)
 	{
 		slot_t *s = &h->slots[seq % h->nslots];
 		pthread_mutex_lock(&h->mu);
-		while (!(s->state == SLOT_DONE && seq < h->seq_filled) && !(h->finishing && seq >= h->seq_filled))
+		while (!h->failed && !(s->state == SLOT_DONE && seq < h->seq_filled) && !(h->finishing && seq >= h->seq_filled))
 			pthread_cond_wait(&h->cv, &h->mu);
-		if (seq >= h->seq_filled)
+		if (h->failed || seq >= h->seq_filled)
 		{
 			pthread_mutex_unlock(&h->mu);
 			return NULL;
@@ -522,9 +588,13 @@ static void *writer_main(void *arg)
 
 		/* strictly in batch order: this is the reference's output file */
 		if (fwrite(s->out, 1, (size_t)s->rows.n * eb, h->fp) != (size_t)s->rows.n * eb)
-			die("Failed to write the output file", NULL);
+		{
+			pipeline_fail(h, "Failed to write the output file", NULL);
+			return NULL;
+		}
 
 		pthread_mutex_lock(&h->mu);
+		h->epochs_written += s->rows.n;
 		s->state = SLOT_FREE;
 		pthread_cond_broadcast(&h->cv);
 		pthread_mutex_unlock(&h->mu);
@@ -538,8 +608,13 @@ static void queue_batch(gpusim_hook *h)
 	cols_t tmp;
 	const double t0 = now_s();
 	pthread_mutex_lock(&h->mu);
-	while (s->state != SLOT_FREE)
+	while (s->state != SLOT_FREE && !h->failed)
 		pthread_cond_wait(&h->cv, &h->mu);
+	if (h->failed)
+	{
+		pthread_mutex_unlock(&h->mu);
+		pipeline_check(h); /* does not return */
+	}
 	h->t_wait += now_s() - t0;
 	tmp = s->rows;
 	s->rows = h->batch;
@@ -750,6 +825,7 @@ void gpusim_hook_epoch(gpusim_hook *h, channel_t *chan, const int *gain)
 	b->n++;
 	if (b->n >= h->flush_at)
 	{
+		pipeline_check(h);
 		flush_batch(h);
 		h->flush_at = 2 * h->flush_at < h->cap_max ? 2 * h->flush_at : h->cap_max;
 	}
@@ -800,14 +876,8 @@ void gpusim_hook_close(gpusim_hook *h)
 	if (!h->dryrun)
 	{
 		int d;
-		pthread_mutex_lock(&h->mu);
-		h->finishing = 1;
-		pthread_cond_broadcast(&h->cv);
-		pthread_mutex_unlock(&h->mu);
-		for (d = 0; d < h->ndev; d++)
-			pthread_join(h->workers[d].thread, NULL);
-		if (h->ndev > 1)
-			pthread_join(h->writer, NULL);
+		pipeline_join(h);
+		pipeline_check(h); /* reports and exits if anything failed */
 		for (d = 0; d < h->ndev; d++)
 			gpusim_destroy(h->workers[d].ctx);
 		for (d = 0; d < h->nslots; d++)

@@ -31,7 +31,9 @@ if [ ! -f "$REF/gpssim.c" ]; then
 fi
 
 mkdir -p "$OUT/data"
-CFLAGS="-O3 -Wall -D_FILE_OFFSET_BITS=64"
+# -ffp-contract=off: a no-op on x86-64 without -march (no FMA to contract into), spelled out so that the
+# goldens mean the same thing on any build machine (see integration/build_host.py)
+CFLAGS="-O3 -Wall -D_FILE_OFFSET_BITS=64 -ffp-contract=off"
 
 # --- as shipped (double carrier phase) ---------------------------------------
 gcc $CFLAGS "$REF/gpssim.c" -lm -o "$OUT/gps-sdr-sim-float"

@@ -115,3 +115,20 @@ def test_chain_walk_property_random_steps_and_moduli():
         assert np.float64(end_w).view(np.uint64) == np.float64(end_g).view(np.uint64)
 
     check()
+
+
+def test_falling_chain_never_jumps_onto_the_binade_edge():
+    """A falling chain that would land exactly on 2^e must take that step as a real addition: below 2^e the
+    grid is twice as fine, so the reference's sum can round to 2^e - ulp/2 where a jump on the coarse grid
+    says 2^e.  x0 = 256 + 3*q*u, d = -(q*u + 0.375*u): three steps, the third one lands on 256."""
+    u = 2.0 ** -44                                   # ulp in [256, 512)
+    for q in (1 << 20, (1 << 30) + 12345, 3):
+        d = -(q * u + 0.375 * u)
+        x0 = 256.0 + 3 * q * u
+        want = np.float64(x0)
+        for _ in range(3):
+            want = want + np.float64(d)
+        assert want < 256.0                          # the reference ends half a (coarse) ulp below the edge
+        got, _, end = emu_lib.phase_chain(x0, d, 512.0, 3, 1)
+        assert np.float64(end).view(np.uint64) == np.float64(want).view(np.uint64)
+        assert np.float64(got[3]).view(np.uint64) == np.float64(want).view(np.uint64)

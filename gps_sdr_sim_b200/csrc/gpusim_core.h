@@ -339,13 +339,12 @@ struct AccF32x2 {
 // K1 - code-phase chain.  The reference advances code_phase by N rounded double adds per
 // epoch and channel (gpssim.c:2212-2218); the samples of an epoch can only be generated
 // in parallel if the exact value is known at the start of every thread's chunk.  This
-// walks the chain without doing N adds: inside one binade [2^e, 2^(e+1)) below the wrap,
-// every "x += d" moves the 53-bit significand of x by the same integer q = RN(d/ulp(x))
-// (round-half-even ties: only from an even significand, where the increment is again
-// constant), so k steps are one 64-bit multiply-add.  Only steps that cross a binade
-// edge or the 1023-chip wrap are executed as real IEEE additions.  ~14 jumps per code
-// period instead of ~2600 adds (2.6 MS/s); bit-exact by construction, and checked against
-// the plain replay in tests/test_chain.py.
+// walks the chain without doing N adds: inside one binade [2^e, 2^(e+1)) every "x += d"
+// moves x by the same multiple of ulp(x), delta = RN_ulp(x)(d), so k steps are ONE fused
+// multiply-add (x + k*delta is representable, hence exact); only the step that crosses a
+// binade edge or the wrap is executed as a real IEEE addition.  ~10 jumps per code period
+// instead of ~2600 adds (2.6 MS/s); bit-exact by construction, and checked against the
+// plain replay in tests/test_chain.py.
 //
 // emit(j, x, wraps) is called for sample indices j*every, j = 0 .. ceil(n_total/every)-1.
 // =====================================================================================
@@ -357,17 +356,24 @@ GS_HD double dfma(double a, double b, double c) // one rounding of the exact a*b
     return __builtin_fma(a, b, c);
 #endif
 }
-
-// The walk is done entirely in FP64: the GPU has no 64-bit integer ALU, but every quantity here
-// (x, the per-binade increment, k increments) is a multiple of ulp(x) below 2^53 ulps, i.e. an
-// exactly representable double, so DADD/DFMA return exact results and one instruction does the
-// work of a multi-instruction 64-bit integer sequence:
-//   delta = (2^e + d) - 2^e   is d rounded to a multiple of ulp(x) exactly as "x + d" rounds it
-//                             (ties go to the even significand, and 2^e has an even one);
-//   x + k*delta               is ONE fma, exact because the result is representable.
-// true if `pred` holds for any thread of `mask` (all of which must call it together); on the host
-// a "warp" is one thread.  Voting also re-converges the threads of the warp.
-GS_HD bool warp_any(unsigned mask, bool pred)
+GS_HD double dadd_down(double a, double b) // a + b rounded towards -infinity (exact sums are not affected)
+{
+#ifdef __CUDA_ARCH__
+    return __dadd_rd(a, b);
+#else
+    // host: only ever called with a in [0, 2^31] and b = 2^52, where the rounded-down sum is 2^52 + floor(a)
+    return b + __builtin_floor(a);
+#endif
+}
+GS_HD int ctz64(uint64_t v) // v != 0
+{
+#ifdef __CUDA_ARCH__
+    return __ffsll((long long)v) - 1;
+#else
+    return __builtin_ctzll(v);
+#endif
+}
+GS_HD bool warp_any(unsigned mask, bool pred) // kept for callers that vote; on the host a "warp" is one thread
 {
 #ifdef __CUDA_ARCH__
     return __any_sync(mask, pred);
@@ -376,6 +382,11 @@ GS_HD bool warp_any(unsigned mask, bool pred)
     return pred;
 #endif
 }
+#if defined(__GNUC__) || defined(__CUDACC__)
+#define GS_UNLIKELY(c) __builtin_expect(!!(c), 0)
+#else
+#define GS_UNLIKELY(c) (c)
+#endif
 
 // Exact walk of the recurrence
 //     x += d;  if (x >= M) x -= M;  else if (x < 0) x += M;          (|d| < M, either sign)
@@ -384,144 +395,99 @@ GS_HD bool warp_any(unsigned mask, bool pred)
 //   code phase    M = 1023, d = RN(f_code*delt) > 0                    gpssim.c:2212-2218
 //   carrier phase M = 512,  d = 512*RN(f_carr*delt), x = 512*carr_phase (FLOAT_CARR_PHASE hosts;
 //                 the power-of-two scaling commutes with every rounding)   gpssim.c:2245-2250
-// `mask`: the threads of the warp that walk chains together (device only).
-// kSign: +1 the caller knows d >= 0 (the code phase), -1 d < 0, 0 decided at run time.  With a known
-// sign the test of the reference that can never fire and the other direction's jump are not compiled in
-// (a real step costs 17 instead of 31 instructions on the device, a jump trip ~20 fewer).
-#if defined(__GNUC__) || defined(__CUDACC__)
-#define GS_UNLIKELY(c) __builtin_expect(!!(c), 0)
-#else
-#define GS_UNLIKELY(c) (c)
-#endif
+// kSign: +1 the caller knows d >= 0 (the code phase), -1 d < 0, 0 decided at run time.
+//
+// One trip of the loop = at most one jump inside the current binade followed by ONE real step (which
+// is the one that crosses the binade edge or wraps).  Why the jump is exact, with u = ulp(x),
+// x in [c, 2c), c = 2^e:
+//   * every sum x + d whose real value stays inside [c, 2c) is rounded on the grid of u, to
+//     x + delta with delta = RN_u(d); ties go to the even significand, and delta computed as
+//     (c + d) - c (rising; (1.5c + d) - 1.5c falling: an anchor with an even significand that keeps
+//     anchor + d inside the binade) rounds them exactly like a sum from an even significand does.  The
+//     one case that rounds the other way - an exact tie from an ODD significand - takes a real step
+//     first; after it the significand is even for good (tie_s: the only binade distance at which d
+//     is a tie is 1 + the number of trailing zero bits of its significand).
+//   * k steps are then x + k*delta, ONE fma: exact because the result is a multiple of u inside the
+//     binade.  The landing must stay STRICTLY inside: at most pred(min(2c, M)) rising, at least
+//     succ(c) falling (on the edge c itself the grid below is twice as fine and the reference's sum
+//     may round to c - u/2).
+//   * k only has to be a LOWER bound of the number of steps that fit: floor(room * r) with
+//     r = (1/|d|) * (1 - 2^(s-50)), s = e - exponent(d).  |delta| differs from |d| by at most u/2, a
+//     relative 2^(s-53), and the roundings of 1/|d| and of the product by 2^-52 each, so room * r <
+//     room / |delta| and the floor never overshoots: no verification, no fix-up.  When it falls
+//     short by a step (probability ~2^(2s-50) per jump) that step is simply taken as a real addition.
+//     The floor is the low word of RD(room * r + 2^52): no conversion instructions on the chain.
 template <int kSign = 0, class Emit>
 GS_HD double phase_chain(double x, const double d, const double M, const int n_end, const int every,
                          Emit emit, const unsigned mask = 0xffffffffu)
 {
-    const bool neg = kSign == 0 ? d < 0.0 : kSign < 0;
-    const double ad = neg ? -d : d;
-    const int ed = (int)((dbits(ad) >> 52) & 0x7ff) - 1023;
-    const double rd = 1.0 / ad; // k = room/|delta| is estimated with 1/|d| and then corrected exactly
-    // bit s set: in a binade with ulp = 2^s * ulp(d), d is exactly half an ulp off a multiple
-    uint32_t tie_shifts = 0;
-    {
-        const uint64_t dm = dbits(ad) & 0xfffffffffffffull;
-        for (int sft = 1; sft <= 30; sft++)
-            if ((dm & ((1ull << sft) - 1)) == (1ull << (sft - 1)))
-                tie_shifts |= 1u << sft;
-    }
+    (void)mask;
+    if (kSign == 0)
+        return d < 0.0 ? phase_chain<-1>(x, d, M, n_end, every, emit) : phase_chain<1>(x, d, M, n_end, every, emit);
+    constexpr bool neg = kSign < 0;
+    const uint64_t db = dbits(neg ? -d : d);
+    const int bex_d = (int)(db >> 52); // biased exponent of |d| (d is finite and normal or zero)
+    const uint64_t dm = db & 0xfffffffffffffull;
+    const int tie_s = dm ? ctz64(dm) + 1 : 0;
+    const double rd = db ? 1.0 / (neg ? -d : d) : 0.0; // d == 0: never used (every step is a real "x += 0")
+    const uint64_t mbits = dbits(M);
     int n = 0, next = every, j = 1, wraps = 0;
 
-    // one genuine step; returns true when it wrapped
-    auto real_step = [&]() -> bool {
-        x = dadd(x, d);
-        bool wrapped = false;
-        if (kSign >= 0 && x >= M) { // a rising chain leaves [0, M) at the top only, a falling one at the bottom
-            x = dadd(x, -M);
-            wrapped = true;
-        } else if (kSign <= 0 && x < 0.0) {
-            x = dadd(x, M);
-            wrapped = true;
+    emit(0, x, 0);
+    while (n < n_end) {
+        const uint64_t xb = dbits(x);
+        const int bex = (int)(xb >> 52); // x is in [0, M): sign bit clear
+        const int shift = bex - bex_d;
+        // jump inside this binade: needs |d| < c/2 (anchor + d stays in the binade), k below 2^31, no odd tie
+        if (shift >= 2 && shift <= 30 && !(shift == tie_s && (xb & 1u)) && db != 0) {
+            const uint64_t cb = (uint64_t)bex << 52; // c = 2^e
+            double delta, room;
+            if (!neg) {
+                const double c = dfrombits(cb);
+                delta = dadd(dadd(c, d), -c);
+                const uint64_t c2b = cb + (1ull << 52);                    // 2c
+                const double top = dfrombits((c2b > mbits ? mbits : c2b) - 1); // pred(min(2c, M))
+                room = dadd(top, -x);
+            } else {
+                const double c15 = dfrombits(cb | (1ull << 51)); // 1.5c
+                delta = dadd(dadd(c15, d), -c15);                // negative
+                room = dadd(x, -dfrombits(cb + 1));              // down to succ(c); -u when x == c
+            }
+            const double r = dfma(-rd, dfrombits((uint64_t)(1023 - 50 + shift) << 52), rd);
+            const double m1 = dadd_down(dmul(room, r), 4503599627370496.0); // 2^52 + floor(room * r)
+            int k = (int)(uint32_t)dbits(m1);
+            double kf = dadd(m1, -4503599627370496.0);
+            if (GS_UNLIKELY(k > n_end - n)) {
+                k = n_end - n;
+                kf = (double)k;
+            }
+            if (k > 0) {
+                // checkpoints that fall inside the jump
+                while (GS_UNLIKELY(next - n <= k)) {
+                    emit(j++, dfma((double)(next - n), delta, x), wraps);
+                    next += every;
+                }
+                x = dfma(kf, delta, x);
+                n += k;
+                if (n >= n_end)
+                    break;
+            }
         }
-        wraps += wrapped ? 1 : 0;
+        // one genuine step: crosses the binade edge, wraps, or walks the binades too small to jump in
+        x = dadd(x, d);
+        if (!neg) { // a rising chain leaves [0, M) at the top only, a falling one at the bottom
+            if (x >= M) {
+                x = dadd(x, -M);
+                wraps++;
+            }
+        } else if (x < 0.0) {
+            x = dadd(x, M);
+            wraps++;
+        }
         n++;
         if (GS_UNLIKELY(n == next)) {
             emit(j++, x, wraps);
             next += every;
-        }
-        return wrapped;
-    };
-    auto shift_of = [&](double v) -> int { return (int)((dbits(v) >> 52) & 0x7ff) - 1023 - ed; };
-
-    // The loops are shaped so that the threads of a warp - the same satellite in 32 consecutive
-    // epochs, i.e. chains that cross the binades and the wrap at nearly the same sample - take the
-    // same number of trips and re-converge once per period: one trip of the outer loop is one
-    // period (code period / carrier cycle), one trip of loop B is one binade (a jump and the real
-    // step across its edge).  The votes keep the warp together (threads that are done idle).
-    emit(0, x, 0);
-    while (warp_any(mask, n < n_end)) {
-        // A: the low binades hold only a handful of steps (2^shift/1.x each): real additions
-        while (n < n_end && shift_of(x) < 4)
-            if (real_step() && neg)
-                break; // a falling chain wraps out of the low binades: continue at the top in B
-        // B: one binade per trip, until the chain wraps (shift <= 30 keeps k inside an int)
-        bool in_period = n < n_end;
-        while (warp_any(mask, in_period)) {
-            if (!in_period)
-                continue;
-            const uint64_t xb = dbits(x);
-            const int bex = (int)((xb >> 52) & 0x7ff); // biased exponent of x
-            const int shift = bex - 1023 - ed;
-            // exact tie (d is half an ulp of x away from a multiple of that ulp): from an odd
-            // significand the rounding goes the other way once - take the real step, after it the
-            // significand is even for good
-            const bool tie_odd = ((tie_shifts >> (shift & 31)) & (uint32_t)xb & 1u) != 0;
-            if (shift >= 4 && shift <= 30 && !tie_odd) {
-                const double c = dfrombits((uint64_t)bex << 52);        // 2^e
-                const double u = dfrombits((uint64_t)(bex - 52) << 52); // ulp(x)
-                int k;
-                double y, delta;
-                bool ok;
-                if (!neg) {
-                    // delta = d rounded to a multiple of ulp(x) exactly as "x + d" rounds it (ties go to
-                    // the even significand, and 2^e has an even one)
-                    delta = dadd(dadd(c, d), -c);
-                    const double c2 = dadd(c, c);
-                    const double top = dadd(c2 > M ? M : c2, -u); // strictly inside the binade, below the wrap
-                    const double room = dadd(top, -x);            // exact, >= 0
-                    k = (int)(room * rd);
-                    y = dfma((double)k, delta, x);
-                    if (y > top) {
-                        k--;
-                        y = dfma((double)k, delta, x);
-                    } else if (dadd(top, -y) >= delta) {
-                        k++;
-                        y = dfma((double)k, delta, x);
-                    }
-                    if (GS_UNLIKELY(k > n_end - n)) {
-                        k = n_end - n;
-                        y = dfma((double)k, delta, x);
-                    }
-                    ok = k > 0 && y <= top;
-                } else {
-                    // falling chain: same with 1.5*2^e as the rounding anchor (even significand, and
-                    // anchor + d stays inside the binade), down to the bottom 2^e inclusive
-                    const double c15 = dfma(0.5, c, c);
-                    delta = dadd(dadd(c15, d), -c15);      // negative
-                    const double room = dadd(x, -c);        // exact, >= 0
-                    k = (int)(room * rd);
-                    y = dfma((double)k, delta, x);
-                    if (y < c) {
-                        k--;
-                        y = dfma((double)k, delta, x);
-                    } else if (dadd(y, -c) >= -delta) {
-                        k++;
-                        y = dfma((double)k, delta, x);
-                    }
-                    if (GS_UNLIKELY(k > n_end - n)) {
-                        k = n_end - n;
-                        y = dfma((double)k, delta, x);
-                    }
-                    // A landing exactly ON the edge 2^e is not a jump: below the edge the grid is twice as
-                    // fine, so the reference's sum may round to 2^e - ulp/2 where the coarse grid says 2^e.
-                    // Stop one step short; the step onto or over the edge is then a real addition.
-                    if (y == c) {
-                        k--;
-                        y = dfma((double)k, delta, x);
-                    }
-                    ok = k > 0 && y > c;
-                }
-                if (ok) {
-                    // checkpoints that fall inside the jump
-                    while (next - n <= k) {
-                        emit(j++, dfma((double)(next - n), delta, x), wraps);
-                        next += every;
-                    }
-                    x = y;
-                    n += k;
-                }
-            }
-            if (n >= n_end || real_step())
-                in_period = false;
         }
     }
     return x;

@@ -4,17 +4,25 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]): the circle.csv scenario's shape - 2999 epochs of 0.1 s,
-13 visible satellites, 2.6 MS/s, 8-bit IQ - as a seeded synthetic epoch table
-(gps_sdr_sim_b200.synthetic_table; there is no way to run the reference's host on the GPU
-box inside this script).  One step = one pass of the hot path over all 2999 epochs
-(779.74 M samples, 1.56 GB of output) on each GPU; with N GPUs the job is N times longer in
-simulated time and time-sharded (weak scaling, no collective on the data path).
+Workload (BASELINE.json configs[1]): the circle.csv scenario - 2999 epochs of 0.1 s, 13 satellites,
+2.6 MS/s, 8-bit IQ.  The rows are the REAL ones: recorded on the box from the reference's own host in
+dry-run mode (gps_sdr_sim_b200/scenarios.py: the bound host runs its RINEX / orbit / code-phase / nav-message
+code and writes the table that would cross the C ABI; no GPU involved), else the committed copy
+bench_data/config2.npz, else - and only then - a seeded synthetic table of the same shape; `data` says which.
+One step = one pass of the hot path over all 2999 epochs (779.74 M samples, 1.56 GB of output) on each
+GPU; with N GPUs every GPU generates the whole 300 s scenario (N x the work, weak scaling, no collective on
+the data path; ONE long job time-sharded over GPUs is tools/bench_config5.py and the CLI's GPUSIM_DEVICES).
 
-`value`  whole-job samples/s with the tables resident in HBM, CUDA events on the launch stream,
-         max over ranks.
-`e2e`    the same metric through gpusim_generate_epochs(): host table in, host bytes out,
-         table compaction + H2D + kernels + D2H inside the timed region.
+`value`    whole-job samples/s with the tables resident in HBM, CUDA events on the launch stream, max over ranks.
+`e2e`      the same metric through gpusim_generate_epochs(): host table in, host bytes out, table compaction +
+           H2D + kernels + D2H inside the timed region.  With N > 1 the N x 2999 epochs are split over the
+           ranks in proportion to each GPU's measured host-link rate (the GPUs of a box do not share the
+           host link evenly).
+`configs`  device-timed K1 / K2 of ONE isolated call for every other BASELINE configuration, on its real rows.
+`roofline` HBM: algorithmic output bytes / CUDA-event duration of the K2 launches.  `issue`: the same launch
+           against the instruction-issue roof, live: algorithmic instructions and - from an ncu pass
+           run by this script after the timed region, on the same box - executed instructions, issue-active and
+           DRAM traffic of one K2 launch of this workload.
 `--impl reference` times the reference's own single-threaded CPU build (oracle/_ref) instead.
 """
 from __future__ import annotations
@@ -24,6 +32,7 @@ import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -35,7 +44,23 @@ N_SAMPLES = 260000       # 2.6 MS/s
 N_ACTIVE = 13
 FMT = 8
 METRIC = "IQ samples/sec (device-timed)"
-WORKLOAD = "config2-shape: 2999 epochs x 13 channels, 2.6 MS/s, 8-bit IQ (circle.csv scenario shape)"
+WORKLOAD = "config 2: -u circle.csv -s 2600000 -b 8, full 300 s (2999 epochs x 13 channels, 2.6 MS/s, 8-bit IQ)"
+# instructions the synthesis kernel cannot do without, per (sample, channel): code-phase add, floor (round-down
+# magic add), chip-window shift, sign fold, index shift, table address, table load, multiply-add (I and Q in
+# one FFMA2), carrier-phase add; per sample: round + pack + store share
+ALG_INSTR_PER_SAMPLE_CHANNEL = 9.0
+ALG_INSTR_PER_SAMPLE = {16: 2.25, 8: 2.5, 1: 3.25}
+
+
+def headline_table(gs):
+    """-> (EpochTable, data description)"""
+    from gps_sdr_sim_b200 import scenarios
+    try:
+        t, how = scenarios.load("config2")
+        assert t.n_epochs == EPOCHS and t.samples_per_epoch == N_SAMPLES and t.data_format == FMT
+        return t, "circle.csv scenario, " + how
+    except (FileNotFoundError, AssertionError, OSError, subprocess.CalledProcessError):
+        return gs.synthetic_table(EPOCHS, N_SAMPLES, N_ACTIVE, FMT), "synthetic (no bound host and no bench_data/config2.npz on this machine)"
 
 
 def rank_env():
@@ -77,6 +102,7 @@ def run_port_once(n_epochs: int):
 
 
 def cpu_baseline(duration_s: float = 45.0):
+    """the reference's CPU build on a bounded sample of the same scenario (its first duration_s seconds)"""
     _, _, ok = ref_paths()
     if ok:
         samples, sec = run_reference_once(duration_s)
@@ -180,21 +206,6 @@ def measured_peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_capture():
-    """figures of the committed ncu --set full capture of the synthesis kernel (profiles/traffic.json)"""
-    p = os.path.join(ROOT, "profiles", "traffic.json")
-    try:
-        with open(p) as f:
-            return json.load(f)
-    except Exception:  # noqa: BLE001
-        return {}
-
-
-def ncu_traffic():
-    """dram bytes per launch of the synthesis kernel from the committed ncu --set full capture."""
-    return ncu_capture().get("k2_synth_sc08_dram_bytes_per_launch")
-
-
 def bind_to_gpu_cpus(index: int):
     """Pin this rank to the CPUs closest to its GPU (NVML's affinity mask) so that the page-locked
     output buffer is allocated on the NUMA node the GPU's PCIe link hangs off.  Best effort."""
@@ -213,7 +224,106 @@ def bind_to_gpu_cpus(index: int):
     return "unbound"
 
 
+def pick_device(local_rank: int, world: int, n_visible: int) -> int:
+    """Spread the ranks over the box's two host roots: on this pool's 8-GPU boxes GPUs 0-3 and 4-7 hang off
+    different PCIe roots (profiles/r01_pcie_8gpu.md), so 2 ranks use GPUs 0,4 and 4 ranks 0,1,4,5.  Only when all
+    8 GPUs are visible; otherwise rank r uses device r."""
+    if n_visible >= 8 and world in (2, 4):
+        half = world // 2
+        return local_rank if local_rank < half else 4 + (local_rank - half)
+    return local_rank
+
+
+def link_rate_gbs(torch, n_bytes: int = 256 << 20) -> float:
+    """this GPU's pinned device-to-host rate right now (all ranks measure at the same time)"""
+    src = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
+    dst = torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        dst.copy_(src, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    return 3 * n_bytes / 1e9 / (e0.elapsed_time(e1) / 1e3)
+
+
+def isolated_call_ms(gs, torch, table, device, repeats: int = 4):
+    """best (K1, K2) CUDA-event durations of ONE generate_device call on resident tables"""
+    out = torch.empty(table.n_epochs * table.epoch_bytes, dtype=torch.uint8, device="cuda")
+    with gs.GpuSim.for_table(table, device=device) as sim:
+        sim.upload_table(table)
+        best = None
+        for _ in range(repeats):
+            sim.generate_device(0, table.n_epochs, out.data_ptr(), out.numel())
+            t = sim.timing()
+            if best is None or t.chain_ms + t.synth_ms < best[0] + best[1]:
+                best = (t.chain_ms, t.synth_ms)
+    del out
+    return best
+
+
+def other_configs(gs, torch, device):
+    """device-timed K1 / K2 of one isolated call for the other BASELINE configurations, real rows"""
+    from gps_sdr_sim_b200 import scenarios
+    res = {}
+    for name in ("config1", "config3_satellite", "config3_rocket", "config4", "config5_batch", "config2_float", "config1_float"):
+        try:
+            t, how = scenarios.load(name)
+        except (FileNotFoundError, OSError, subprocess.CalledProcessError) as exc:
+            res[name] = {"unavailable": f"{type(exc).__name__}"}
+            continue
+        k1, k2 = isolated_call_ms(gs, torch, t, device)
+        samples = t.n_epochs * t.samples_per_epoch
+        fs = 10.0 * t.samples_per_epoch
+        res[name] = {"what": scenarios.SCENARIOS[name][2], "epochs": t.n_epochs, "channels_max": t.max_active(),
+                     "iq_bits": t.data_format, "carrier": "double (as shipped)" if t.carrier_mode else "integer",
+                     "k1_chain_ms": round(k1, 4), "k2_synth_ms": round(k2, 4),
+                     "samples_per_s": samples / ((k1 + k2) / 1e3), "x_realtime": samples / ((k1 + k2) / 1e3) / fs,
+                     "k2_gsample_channels_per_s": float((t.cols["prn"] > 0).sum()) * t.samples_per_epoch / (k2 / 1e3) / 1e9,
+                     "k2_output_gb_per_s": t.n_epochs * t.epoch_bytes / 1e9 / (k2 / 1e3)}
+    return res
+
+
+def ncu_live(table_path: str, timeout_s: int = 240):
+    """One K2 launch of the bench workload under ncu, on this box, after the timed region: executed
+    instructions, issue-active, DRAM bytes.  -> dict or {"unavailable": why}"""
+    import csv
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return {"unavailable": "ncu not found"}
+    metrics = ["smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+               "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum", "sm__cycles_elapsed.avg",
+               "smsp__cycles_active.avg"]
+    cmd = [ncu, "--csv", "--clock-control", "none", "--metrics", ",".join(metrics), "-k", "regex:k2_", "--launch-skip", "1",
+           "--launch-count", "1", sys.executable, os.path.join(ROOT, "tools", "profile_one.py"), "--table", table_path]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s)
+    except (subprocess.TimeoutExpired, OSError) as exc:
+        return {"unavailable": f"{type(exc).__name__}"}
+    rows = [row for row in csv.reader(r.stdout.splitlines()) if len(row) > 6]
+    if r.returncode != 0 or len(rows) < 2:
+        return {"unavailable": "ncu pass failed: " + (r.stderr.strip().splitlines() or ["no output"])[-1][:200]}
+    hdr = rows[0]
+    ix = {h: i for i, h in enumerate(hdr)}
+    out = {}
+    for row in rows[1:]:
+        try:
+            v = float(row[ix["Metric Value"]].replace(",", ""))
+        except ValueError:
+            continue
+        unit = row[ix["Metric Unit"]]
+        v *= {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "msecond": 1e-3, "usecond": 1e-6, "nsecond": 1e-9}.get(unit, 1.0)
+        out[row[ix["Metric Name"]]] = v
+        out["kernel"] = row[ix["Kernel Name"]]
+    return out
+
+
 def main_b200(args):
+    import hashlib
+
     import torch
     import torch.distributed as dist
     import gps_sdr_sim_b200 as gs
@@ -224,27 +334,25 @@ def main_b200(args):
             raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - this path has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    numa = bind_to_gpu_cpus(local_rank)    # before any pinned allocation: keep staging memory NUMA-local
+    device = pick_device(local_rank, world, torch.cuda.device_count())
+    torch.cuda.set_device(device)
+    numa = bind_to_gpu_cpus(device)    # before any pinned allocation: keep staging memory NUMA-local
     if world > 1:
         # stdout of rank 0 is ONE JSON line: NCCL_DEBUG=VERSION (set on some boxes) makes NCCL print its version there
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", device))
 
-    # weak scaling: the job is `world` times longer in simulated time; rank r owns a contiguous
-    # epoch range.  Every rank builds the same seeded table and keeps its slice.
-    from gps_sdr_sim_b200.shard import epoch_range
-    table_all = gs.synthetic_table(EPOCHS * world, N_SAMPLES, N_ACTIVE, FMT)
-    first, count = epoch_range(rank, world, table_all.n_epochs)
-    table = table_all.slice(first, count)
-    del table_all
+    # weak scaling: every GPU generates the whole scenario (identical real rows on every rank)
+    table, data_how = headline_table(gs)
+    count = table.n_epochs
     eb = table.epoch_bytes
     out_bytes = count * eb
+    sample_channels = float((table.cols["prn"] > 0).sum()) * N_SAMPLES
 
-    sim = gs.GpuSim(N_SAMPLES, table.delt, FMT, gs.CARRIER_INT, max_batch_epochs=count, device=local_rank)
-    if args.no_pipeline:
-        sim.set_option("pipeline", 0)
+    sim = gs.GpuSim(N_SAMPLES, table.delt, FMT, gs.CARRIER_INT, max_batch_epochs=count, device=device)
+    if args.pipeline is not None:
+        sim.set_option("pipeline", args.pipeline)
     sim.upload_table(table)                      # tables resident in HBM before the timed region
     out = torch.empty(out_bytes, dtype=torch.uint8, device="cuda")
     stream = torch.cuda.Stream()                 # a real stream: calls are asynchronous and pipeline
@@ -257,47 +365,73 @@ def main_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(device)
     sampler.start()
     sampler.ready.wait(timeout=20)
     for _ in range(args.warmup):
         step()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k1_ms = []
     w0 = time.perf_counter()
     ev0.record(stream)
-    marks = [ev0]                                # one event between consecutive steps, on the launch stream
     for i in range(args.steps):
         step()
-        if i + 1 < args.steps:
-            marks.append(torch.cuda.Event(enable_timing=True))
-            marks[-1].record(stream)
     ev1.record(stream)
-    marks.append(ev1)
     barrier()
     w1 = time.perf_counter()
     clocks = sampler.window(w0, w1)
     ms = ev0.elapsed_time(ev1)
-    # per-kernel durations of the last step (CUDA events recorded by the library on the same stream)
+    # per-kernel durations of the last step (CUDA events recorded by the library around its launches, on the
+    # streams they were launched on)
     t = sim.timing()
-    k1_ms.append(t.chain_ms)
-    k2_last_ms = t.synth_ms
-    # Average duration of the synthesis kernel's launches over the timed region.  With the chain kernel
-    # of the next step on the library's own stream, the launch stream carries nothing but the K2
-    # launches (they follow each other within 3 us, tools/step_gap.py), so the time between two marks
-    # is one K2 launch - including what the co-running chain kernel costs it, which the library's own
-    # event pair of the LAST step (no chain kernel beside it any more) does not show.  Without the
-    # overlap the chain kernel runs on the launch stream as well and is subtracted.
-    per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(len(marks) - 1)]
-    k2_ms = [m - (t.chain_ms if args.no_pipeline else 0.0) for m in per_step]
+    k1_last_ms, k2_last_ms = t.chain_ms, t.synth_ms
+    overlapped = bool(t.chain_overlapped) if hasattr(t, "chain_overlapped") else None
+    # average duration of the synthesis kernel's launches over the timed region: the launch stream carries the
+    # K2 launches back to back (and the chain kernels too unless the library runs them on its own stream)
+    k2 = ms / args.steps - (0.0 if overlapped else k1_last_ms)
     launches_per_step = t.launches
     fast_path = t.fast_path
 
+    # ---- the timed output is the reference's: SHA-256 of sampled epochs against the oracle (outside the timed region)
+    check = {"epochs": [], "sha256_matches_oracle": None}
+    if rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        try:
+            import oracle_lib
+            ok = True
+            for e in (0, count // 2, count - 1):
+                got = out[e * eb:(e + 1) * eb].cpu().numpy().tobytes()
+                want = oracle_lib.generate(table, e, 1).tobytes()
+                check["epochs"].append(e)
+                ok = ok and hashlib.sha256(got).digest() == hashlib.sha256(want).digest()
+            check["sha256_matches_oracle"] = ok
+        except Exception as exc:  # noqa: BLE001 - the checker is optional equipment, a mismatch is not
+            check["unavailable"] = f"{type(exc).__name__}: {exc}"
+        if check["sha256_matches_oracle"] is False:
+            raise SystemExit("bench.py: the timed output differs from the oracle - refusing to report a number")
+
     # ---- e2e: host table in, host bytes out, through the public C-ABI call ----------------------
-    host_out = torch.empty(out_bytes, dtype=torch.uint8, pin_memory=True)
+    # N x 2999 epochs in total; with N > 1 each rank's share follows its measured host-link rate
+    share = count
+    rates = None
+    if world > 1:
+        mine = torch.tensor([link_rate_gbs(torch)], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        rates = [float(r) for r in allr]
+        total = count * world
+        shares = [max(1, min(count, int(total * r / sum(rates)))) for r in rates]
+        # epochs capped at one table per rank; what the caps cut off goes to the ranks with room, fastest first
+        left = total - sum(shares)
+        for i in sorted(range(world), key=lambda i: -rates[i]):
+            add = min(left, count - shares[i])
+            shares[i] += add
+            left -= add
+        share = shares[rank]
+    e2e_table = table.slice(0, share)
+    host_out = torch.empty(share * eb, dtype=torch.uint8, pin_memory=True)
     def e2e_step():
-        sim.generate_epochs(table, out_ptr=host_out.data_ptr(), out_capacity=host_out.numel())
+        sim.generate_epochs(e2e_table, out_ptr=host_out.data_ptr(), out_capacity=host_out.numel())
     for _ in range(min(2, args.warmup)):
         e2e_step()
     barrier()
@@ -306,59 +440,102 @@ def main_b200(args):
         e2e_step()
     torch.cuda.synchronize()
     e2e_sec = time.perf_counter() - t0
-    checksum = int(host_out[:: max(1, out_bytes // 65536)].to(torch.int64).sum())   # result is really on the host
+    checksum = int(host_out[:: max(1, host_out.numel() // 65536)].to(torch.int64).sum())   # result is really on the host
+    e2e_ok = None
+    if rank == 0:
+        try:
+            e2e_ok = bool(hashlib.sha256(host_out[(share - 1) * eb:share * eb].numpy().tobytes()).digest() ==
+                          hashlib.sha256(oracle_lib.generate(table, share - 1, 1).tobytes()).digest())
+        except Exception:  # noqa: BLE001
+            pass
     sampler.stop()
 
+    e2e_epochs = float(share)
     if world > 1:
         tm = torch.tensor([ms, e2e_sec * 1000.0], dtype=torch.float64, device="cuda")
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         ms, e2e_ms = float(tm[0]), float(tm[1])
+        tot = torch.tensor([e2e_epochs], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        e2e_epochs = float(tot[0])
     else:
         e2e_ms = e2e_sec * 1000.0
 
     if rank == 0:
-        total_samples = float(EPOCHS) * world * N_SAMPLES * args.steps
+        total_samples = float(count) * world * N_SAMPLES * args.steps
         value = total_samples / (ms / 1000.0)
-        e2e_value = total_samples / (e2e_ms / 1000.0)
+        e2e_value = e2e_epochs * N_SAMPLES * args.steps / (e2e_ms / 1000.0)
         peak, peak_src = measured_peak_hbm()
-        k2 = sum(k2_ms) / len(k2_ms)
         achieved = (out_bytes / 1e9) / (k2 / 1000.0)
-        h2d = count * 16 * 40 + count       # DevRow 32 B + x0 8 B per slot, + active-channel count
+        h2d = share * 16 * 40 + share       # DevRow 32 B + x0 8 B per slot, + active-channel count
+        props = torch.cuda.get_device_properties(device)
+        sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965
+        issue_peak = props.multi_processor_count * 4 * sm_mhz * 1e6            # warp instructions per second
+        alg_warp_instr = (sample_channels * ALG_INSTR_PER_SAMPLE_CHANNEL + float(count) * N_SAMPLES * ALG_INSTR_PER_SAMPLE[FMT]) / 32.0
+        issue = {"bound": "issue", "unit": "warp instructions/s", "peak": issue_peak,
+                 "peak_source": f"{props.multi_processor_count} SMs x 4 schedulers x {sm_mhz} MHz (median SM clock sampled during the timed region)",
+                 "algorithmic_warp_instructions_per_launch": alg_warp_instr,
+                 "algorithmic_thread_instructions_per_sample_channel": ALG_INSTR_PER_SAMPLE_CHANNEL,
+                 "achieved": alg_warp_instr / (k2 / 1e3), "frac": alg_warp_instr / (k2 / 1e3) / issue_peak}
+        traffic = None
+        if world == 1 and not args.no_ncu:
+            with tempfile.TemporaryDirectory(prefix="bench_ncu_") as tmp:
+                tp = os.path.join(tmp, "table.npz")
+                table.save_npz(tp)
+                sim.close()                     # the profiled process gets the GPU to itself
+                live = ncu_live(tp)
+            if "unavailable" in live:
+                issue["ncu"] = live
+            else:
+                inst = live.get("smsp__inst_executed.sum")
+                traffic = int(live.get("dram__bytes_read.sum", 0) + live.get("dram__bytes_write.sum", 0)) or None
+                issue["ncu"] = {"how": "ncu --metrics ... -k regex:k2_ --launch-count 1 python tools/profile_one.py --table <this run's table>, same box, after the timed region",
+                                "kernel": live.get("kernel"),
+                                "executed_warp_instructions": inst,
+                                "executed_thread_instructions_per_sample_channel": inst * 32.0 / sample_channels if inst else None,
+                                "issue_active_frac": (live.get("smsp__issue_active.avg.pct_of_peak_sustained_active") or 0.0) / 100.0 or None,
+                                "launch_ms_under_ncu": (live.get("gpu__time_duration.sum") or 0.0) * 1e3 or None,
+                                "dram_bytes_read": live.get("dram__bytes_read.sum"), "dram_bytes_write": live.get("dram__bytes_write.sum")}
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32/f64", "data": data_how,
             "config": {"workload": WORKLOAD, "epochs_per_gpu": count, "samples_per_epoch": N_SAMPLES,
-                       "channels": N_ACTIVE, "iq_bits": FMT, "carrier": "integer (gpssim.h:4 disabled)",
+                       "channels": int(table.max_active()), "iq_bits": FMT, "carrier": "integer (gpssim.h:4 disabled)",
                        "cache": "each step writes 1.56 GB per GPU, 12x the 126 MB L2; inputs are tables of 2 MB",
-                       "sharding": "time (epoch ranges), no collective"},
+                       "sharding": "every GPU generates the whole scenario (weak scaling), no collective",
+                       "devices": [pick_device(r, world, torch.cuda.device_count()) for r in range(world)],
+                       "same_rows_as_reference_arm": "yes - both arms run -u circle.csv -s 2600000 -b 8; the reference arm is timed on its first 20 s per step"},
             "x_realtime": value / (10.0 * N_SAMPLES),
             "clocks": clocks,
+            "output_check": check,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": out_bytes, "ms_per_step": e2e_ms / args.steps,
+                    "d2h_bytes_per_step": share * eb, "ms_per_step": e2e_ms / args.steps,
                     "x_realtime": e2e_value / (10.0 * N_SAMPLES), "api": "gpusim_generate_epochs (C ABI), pinned host output",
-                    "rank0_cpu_binding": numa,
-                    "host_checksum": checksum},
+                    "rank0_cpu_binding": numa, "host_checksum": checksum, "last_epoch_matches_oracle": e2e_ok,
+                    "epochs_all_ranks": e2e_epochs,
+                    "link_rates_gbs": rates, "split": "equal" if rates is None else "epochs per rank proportional to the measured pinned D2H rate of its GPU"},
             "gpu_launches": launches_per_step * args.steps,
-            "kernels": {"k1_chain_ms": sum(k1_ms) / len(k1_ms), "k2_synth_ms": k2, "k2_synth_last_step_ms": k2_last_ms,
-                        "tuned_kernel": bool(fast_path),
-                        "chain_overlaps_previous_synth": not args.no_pipeline},
+            "kernels": {"k1_chain_ms": k1_last_ms, "k2_synth_ms": k2, "k2_synth_last_step_ms": k2_last_ms,
+                        "tuned_kernel": bool(fast_path), "chain_overlaps_previous_synth": overlapped},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "peak_source": peak_src,
-                         "kernel": "k2_synth<8,32>", "algorithmic_bytes_per_launch": out_bytes,
-                         "issue": {"active_frac_ncu": (ncu_capture().get("issue_active_pct") or 0.0) / 100.0 or None,
-                                   "thread_instructions_per_sample_channel_ncu":
-                                       ncu_capture().get("thread_instructions_per_sample_channel"),
-                                   "source": "profiles/r01_k2_synth_sc08_ncu.md (not measured live)"},
+                         "traffic": traffic, "peak_source": peak_src,
+                         "kernel": (issue.get("ncu") or {}).get("kernel") or "k2_lean<8,32>", "algorithmic_bytes_per_launch": out_bytes,
+                         "issue": issue,
                          "note": "2 B/sample (SC08) x samples per launch / average CUDA-event duration of the K2 launches of the timed region; "
-                                 "the kernel is instruction-issue bound (INT/FP64/LDS per sample and channel), see DESIGN.md"},
+                                 "the kernel is instruction-issue bound (INT/FP64/LDS per sample and channel, 13 channels per 2 output bytes): "
+                                 "`issue` is the same launch against the issue roof, see DESIGN.md"},
         }
-        if world == 1:
-            line["cpu_baseline"] = cpu_baseline()
+        if world == 1 and not args.no_configs:
+            if sim is not None:
+                sim.close()
+            line["configs"] = other_configs(gs, torch, device)
+        line["cpu_baseline"] = cpu_baseline(45.0 if world == 1 else 10.0)
         print(json.dumps(line), flush=True)
 
     sim.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
@@ -369,7 +546,9 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-pipeline", action="store_true", help="A/B: chain kernel on the caller's stream, no overlap between steps")
+    ap.add_argument("--pipeline", type=int, default=None, help="library option `pipeline` (A/B: 0 = chain kernel always on the caller's stream)")
+    ap.add_argument("--no-ncu", action="store_true", help="skip the ncu pass that measures executed instructions / issue-active / DRAM bytes")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-configuration K1/K2 block")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3          # timing rule: at least three untimed passes

@@ -36,7 +36,7 @@ class _Config(ctypes.Structure):
 
 class Timing(ctypes.Structure):
     _fields_ = [("chain_ms", ctypes.c_float), ("synth_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
-                ("launches", ctypes.c_int32), ("fast_path", ctypes.c_int32)]
+                ("launches", ctypes.c_int32), ("fast_path", ctypes.c_int32), ("chain_overlapped", ctypes.c_int32)]
 
 
 SINK_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
@@ -47,7 +47,7 @@ EXPORTS = (
     "gpusim_epoch_bytes", "gpusim_generate_epochs", "gpusim_generate_epochs_to_sink",
     "gpusim_upload_table", "gpusim_generate_device", "gpusim_get_timing", "gpusim_set_option",
     "gpusim_carrier_lut", "gpusim_ca_code", "gpusim_pack_nav_bits", "gpusim_advance_carrier_f64",
-    "gpusim_host_alloc", "gpusim_host_free",
+    "gpusim_host_alloc", "gpusim_host_free", "gpusim_debug_guard_violations",
 )
 
 
@@ -99,6 +99,8 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.gpusim_host_alloc.argtypes = [sz]
     lib.gpusim_host_free.restype = None
     lib.gpusim_host_free.argtypes = [vp]
+    lib.gpusim_debug_guard_violations.restype = i64
+    lib.gpusim_debug_guard_violations.argtypes = [vp]
     lib.gpusim_advance_carrier_f64.restype = ctypes.c_double
     lib.gpusim_advance_carrier_f64.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_double, i32]
     _lib = lib
@@ -218,6 +220,10 @@ class GpuSim:
         """out_ptr: 16-byte aligned device pointer (e.g. torch tensor .data_ptr()); stream: cudaStream_t."""
         self._check(self._lib.gpusim_generate_device(self._ctx, first_epoch, n_epochs, out_ptr, out_capacity,
                                                      stream))
+
+    def guard_violations(self) -> int:
+        """gpusim_debug_guard_violations: 0 = nothing wrote outside the context's device buffers (needs GPUSIM_GUARD=1)."""
+        return int(self._lib.gpusim_debug_guard_violations(self._ctx))
 
     def timing(self) -> Timing:
         t = Timing()

@@ -75,6 +75,13 @@ struct gpusim_ctx {
     int opt_direct_first_mb = 16, opt_direct_mb = 64; // sub-batch sizes when copying straight into the caller's buffer
 
     gpusim_timing timing{};
+
+    // every device allocation of the context; with GPUSIM_GUARD=1 in the environment each one sits between
+    // two poisoned guard bands that gpusim_debug_guard_violations() checks (memory-safety evidence for the
+    // kernels' writes where compute-sanitizer is not available)
+    struct DevAlloc { unsigned char *base; unsigned char *user; size_t bytes; };
+    std::vector<DevAlloc> allocs;
+    bool guard = false;
 };
 
 namespace {
@@ -91,6 +98,32 @@ int fail(gpusim_ctx *ctx, int status, const char *fmt, ...)
     else
         g_create_error = buf;
     return status;
+}
+
+constexpr size_t kGuardBytes = 4096;
+constexpr int kGuardPoison = 0xA5;
+
+template <class T>
+cudaError_t dev_alloc(gpusim_ctx *ctx, T **out, size_t bytes)
+{
+    bytes = std::max<size_t>(bytes, 16);
+    const size_t pad = ctx->guard ? kGuardBytes : 0;
+    unsigned char *base = nullptr;
+    cudaError_t e = cudaMalloc(&base, bytes + 2 * pad);
+    if (e != cudaSuccess)
+        return e;
+    if (pad) {
+        e = cudaMemset(base, kGuardPoison, pad);
+        if (e == cudaSuccess)
+            e = cudaMemset(base + pad + bytes, kGuardPoison, pad);
+        if (e != cudaSuccess) {
+            cudaFree(base);
+            return e;
+        }
+    }
+    ctx->allocs.push_back({base, base + pad, bytes});
+    *out = reinterpret_cast<T *>(base + pad);
+    return cudaSuccess;
 }
 
 #define GS_CUDA(ctx, call)                                                                     \
@@ -118,7 +151,7 @@ int pick_chunk(const gpusim_ctx *ctx, int n_epochs)
 int ensure_out(gpusim_ctx *ctx)
 {
     if (ctx->d_out == nullptr)
-        GS_CUDA(ctx, cudaMalloc(&ctx->d_out, std::max<size_t>(16, (size_t)ctx->cfg.max_batch_epochs * ctx->epoch_bytes)));
+        GS_CUDA(ctx, dev_alloc(ctx, &ctx->d_out, (size_t)ctx->cfg.max_batch_epochs * ctx->epoch_bytes));
     return GPUSIM_OK;
 }
 
@@ -260,6 +293,7 @@ int launch_range(gpusim_ctx *ctx, int first, int n, uint8_t *out_dev, cudaStream
     ctx->last_slot = slot;
     ctx->timing.launches += 2;
     ctx->timing.fast_path = (which != SynthKernel::Generic) ? 1 : 0;
+    ctx->timing.chain_overlapped = overlap ? 1 : 0;
     return GPUSIM_OK;
 }
 
@@ -332,13 +366,8 @@ void gpusim_destroy(gpusim_ctx *ctx)
     if (ctx->s_chain) cudaStreamSynchronize(ctx->s_chain);
     if (ctx->s_compute) cudaStreamSynchronize(ctx->s_compute);
     if (ctx->s_copy) cudaStreamSynchronize(ctx->s_copy);
-    cudaFree(ctx->d_lut); cudaFree(ctx->d_lut_f32); cudaFree(ctx->d_sin16); cudaFree(ctx->d_cos16); cudaFree(ctx->d_negw);
-    cudaFree(ctx->d_rows); cudaFree(ctx->d_nch); cudaFree(ctx->d_x0);
-    for (int i = 0; i < 2; i++) {
-        cudaFree(ctx->d_ck_x[i]); cudaFree(ctx->d_ck_w[i]); cudaFree(ctx->d_ck_c[i]);
-    }
-    cudaFree(ctx->d_work); cudaFree(ctx->d_out);
-    cudaFree(ctx->d_dc); cudaFree(ctx->d_cph0);
+    for (const gpusim_ctx::DevAlloc &a : ctx->allocs)
+        cudaFree(a.base);
     cudaFreeHost(ctx->h_dc); cudaFreeHost(ctx->h_cph0);
     cudaFreeHost(ctx->h_rows); cudaFreeHost(ctx->h_nch); cudaFreeHost(ctx->h_x0);
     cudaFreeHost(ctx->h_stage[0]); cudaFreeHost(ctx->h_stage[1]);
@@ -376,6 +405,10 @@ int gpusim_create(const gpusim_config *cfg, gpusim_ctx **out_ctx)
 
     gpusim_ctx *ctx = new gpusim_ctx();
     ctx->cfg = *cfg;
+    {
+        const char *g = getenv("GPUSIM_GUARD");
+        ctx->guard = g != nullptr && atoi(g) != 0;
+    }
     const int N = cfg->samples_per_epoch;
     ctx->epoch_bytes = cfg->data_format == GPUSIM_SC01 ? (size_t)(N / 4) : cfg->data_format == GPUSIM_SC08 ? (size_t)2 * N : (size_t)4 * N;
 
@@ -423,12 +456,12 @@ int gpusim_create(const gpusim_config *cfg, gpusim_ctx **out_ctx)
             for (int i = 0; i < kCaWords; i++)
                 negw[(size_t)prn * kCaWords + i] = ~w[i]; // bit set = chip 0 = codeCA -1 (gpssim.c:2241)
         }
-        GS_CREATE(cudaMalloc(&ctx->d_lut, sizeof(lut)));
-        GS_CREATE(cudaMalloc(&ctx->d_lut_f32, sizeof(lut2)));
+        GS_CREATE(dev_alloc(ctx, &ctx->d_lut, sizeof(lut)));
+        GS_CREATE(dev_alloc(ctx, &ctx->d_lut_f32, sizeof(lut2)));
         GS_CREATE(cudaMemcpy(ctx->d_lut_f32, lut2, sizeof(lut2), cudaMemcpyHostToDevice));
-        GS_CREATE(cudaMalloc(&ctx->d_sin16, sizeof(s16)));
-        GS_CREATE(cudaMalloc(&ctx->d_cos16, sizeof(c16)));
-        GS_CREATE(cudaMalloc(&ctx->d_negw, negw.size() * sizeof(uint32_t)));
+        GS_CREATE(dev_alloc(ctx, &ctx->d_sin16, sizeof(s16)));
+        GS_CREATE(dev_alloc(ctx, &ctx->d_cos16, sizeof(c16)));
+        GS_CREATE(dev_alloc(ctx, &ctx->d_negw, negw.size() * sizeof(uint32_t)));
         GS_CREATE(cudaMemcpy(ctx->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
         GS_CREATE(cudaMemcpy(ctx->d_sin16, s16, sizeof(s16), cudaMemcpyHostToDevice));
         GS_CREATE(cudaMemcpy(ctx->d_cos16, c16, sizeof(c16), cudaMemcpyHostToDevice));
@@ -436,9 +469,9 @@ int gpusim_create(const gpusim_config *cfg, gpusim_ctx **out_ctx)
     }
 
     const size_t rows = (size_t)cfg->max_batch_epochs * kMaxChan;
-    GS_CREATE(cudaMalloc(&ctx->d_rows, rows * sizeof(DevRow)));
-    GS_CREATE(cudaMalloc(&ctx->d_nch, (size_t)cfg->max_batch_epochs));
-    GS_CREATE(cudaMalloc(&ctx->d_x0, rows * sizeof(double)));
+    GS_CREATE(dev_alloc(ctx, &ctx->d_rows, rows * sizeof(DevRow)));
+    GS_CREATE(dev_alloc(ctx, &ctx->d_nch, (size_t)cfg->max_batch_epochs));
+    GS_CREATE(dev_alloc(ctx, &ctx->d_x0, rows * sizeof(double)));
     GS_CREATE(cudaMallocHost(&ctx->h_rows, rows * sizeof(DevRow)));
     GS_CREATE(cudaMallocHost(&ctx->h_nch, (size_t)cfg->max_batch_epochs));
     GS_CREATE(cudaMallocHost(&ctx->h_x0, rows * sizeof(double)));
@@ -451,15 +484,15 @@ int gpusim_create(const gpusim_config *cfg, gpusim_ctx **out_ctx)
         ctx->min_chunk *= 2;
     const size_t cks = rows * (size_t)kc_for(N, ctx->min_chunk);
     for (int i = 0; i < 2; i++) {
-        GS_CREATE(cudaMalloc(&ctx->d_ck_x[i], cks * sizeof(double)));
-        GS_CREATE(cudaMalloc(&ctx->d_ck_w[i], cks * sizeof(uint16_t)));
+        GS_CREATE(dev_alloc(ctx, &ctx->d_ck_x[i], cks * sizeof(double)));
+        GS_CREATE(dev_alloc(ctx, &ctx->d_ck_w[i], cks * sizeof(uint16_t)));
         if (cf)
-            GS_CREATE(cudaMalloc(&ctx->d_ck_c[i], cks * sizeof(double)));
+            GS_CREATE(dev_alloc(ctx, &ctx->d_ck_c[i], cks * sizeof(double)));
     }
-    GS_CREATE(cudaMalloc(&ctx->d_work, 64));
+    GS_CREATE(dev_alloc(ctx, &ctx->d_work, 64));
     if (cf) {
-        GS_CREATE(cudaMalloc(&ctx->d_dc, rows * sizeof(double)));
-        GS_CREATE(cudaMalloc(&ctx->d_cph0, rows * sizeof(double)));
+        GS_CREATE(dev_alloc(ctx, &ctx->d_dc, rows * sizeof(double)));
+        GS_CREATE(dev_alloc(ctx, &ctx->d_cph0, rows * sizeof(double)));
         GS_CREATE(cudaMallocHost(&ctx->h_dc, rows * sizeof(double)));
         GS_CREATE(cudaMallocHost(&ctx->h_cph0, rows * sizeof(double)));
     }
@@ -597,6 +630,24 @@ int gpusim_generate_device(gpusim_ctx *ctx, int32_t first, int32_t n, void *out_
     if (!stream)
         GS_CUDA(ctx, cudaStreamSynchronize(s));
     return GPUSIM_OK;
+}
+
+int64_t gpusim_debug_guard_violations(gpusim_ctx *ctx)
+{
+    if (!ctx || !ctx->guard)
+        return -1;
+    if (cudaSetDevice(ctx->cfg.device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)
+        return -2;
+    std::vector<unsigned char> band(2 * kGuardBytes);
+    int64_t bad = 0;
+    for (const gpusim_ctx::DevAlloc &a : ctx->allocs) {
+        if (cudaMemcpy(band.data(), a.base, kGuardBytes, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(band.data() + kGuardBytes, a.user + a.bytes, kGuardBytes, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return -2;
+        for (unsigned char b : band)
+            bad += b != (unsigned char)kGuardPoison;
+    }
+    return bad;
 }
 
 int gpusim_get_timing(const gpusim_ctx *cctx, gpusim_timing *out)

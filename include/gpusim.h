@@ -117,6 +117,7 @@ typedef struct gpusim_timing {
     float total_ms;      /* first kernel start to last kernel end */
     int32_t launches;    /* kernels launched by the call */
     int32_t fast_path;   /* 1 = tuned kernel, 0 = generic kernel was needed */
+    int32_t chain_overlapped; /* 1 = the chain kernel ran on the library's own stream beside the previous call's synthesis kernel */
 } gpusim_timing;
 
 int gpusim_abi_version(void);
@@ -160,6 +161,13 @@ int gpusim_generate_device(gpusim_ctx *ctx, int32_t first_epoch, int32_t n_epoch
                            void *out_device, size_t out_capacity, void *stream);
 
 int gpusim_get_timing(const gpusim_ctx *ctx, gpusim_timing *out);
+
+/* Test facility.  A context created with GPUSIM_GUARD=1 in the environment places every device buffer it
+ * owns (rows, code-phase checkpoints, work counters, its own output buffer) between two 4 KiB poisoned guard
+ * bands.  Returns the number of guard bytes that no longer hold the poison after all work of the context has
+ * finished (0 = no kernel wrote outside its buffers), -1 if the context was created without guards, -2 on a
+ * CUDA error.  The caller's own output buffer (gpusim_generate_device) is the caller's to guard. */
+int64_t gpusim_debug_guard_violations(gpusim_ctx *ctx);
 
 /* Tuning / test hooks (all optional).  key/value pairs documented in DESIGN.md:
  *   "chunk"  samples per thread chunk (multiple of 32), 0 = auto

@@ -40,7 +40,7 @@ def test_library_is_the_in_tree_cuda_build():
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(api._Config) == 32
-    assert ctypes.sizeof(api.Timing) == 20
+    assert ctypes.sizeof(api.Timing) == 24
     from gps_sdr_sim_b200.table import CEpochTable
     assert ctypes.sizeof(CEpochTable) == 8 + 10 * 8
 

@@ -76,10 +76,18 @@ def random_table():
     return t, opts, note
 
 
+GUARD = 4096          # poisoned bytes either side of the caller's device output buffer
+POISON = 0xA5
+
+
 def sweep(cases, seed, verbose=True):
-    """Run `cases` random cases; returns the description of the first mismatch, or None."""
+    """Run `cases` random cases; returns the description of the first mismatch, or None.
+    Memory safety rides along: the library's device buffers sit between poisoned guard bands (GPUSIM_GUARD=1,
+    gpusim_debug_guard_violations) and so does the caller's device output buffer; any byte of a band that
+    changes counts as a mismatch."""
     global rng
     rng = np.random.default_rng(seed)
+    os.environ["GPUSIM_GUARD"] = "1"
     stream = torch.cuda.Stream()
     for case in range(cases):
         t, opts, note = random_table()
@@ -97,7 +105,9 @@ def sweep(cases, seed, verbose=True):
                 got = np.frombuffer(b"".join(chunks), dtype=np.uint8)
             else:   # device-resident, three unsynchronised calls on a side stream over random sub-ranges
                 sim.upload_table(t)
-                buf = torch.zeros(max(16, t.n_epochs * eb), dtype=torch.uint8, device="cuda")
+                whole = torch.full((max(16, t.n_epochs * eb) + 2 * GUARD,), POISON, dtype=torch.uint8, device="cuda")
+                buf = whole[GUARD:whole.numel() - GUARD]
+                buf.zero_()
                 cuts = sorted(set([0, t.n_epochs] + [int(x) for x in rng.integers(0, t.n_epochs + 1, size=2)]))
                 torch.cuda.synchronize()
                 ok_align = all((a * eb) % 16 == 0 for a in cuts[:-1])
@@ -107,7 +117,13 @@ def sweep(cases, seed, verbose=True):
                     sim.generate_device(a, b - a, buf.data_ptr() + a * eb, buf.numel() - a * eb, stream=stream.cuda_stream)
                 stream.synchronize()
                 got = buf[: t.n_epochs * eb].cpu().numpy()
+                stray = int((whole[:GUARD] != POISON).sum()) + int((whole[whole.numel() - GUARD:] != POISON).sum())
+                if stray:
+                    return f"case {case}: {stray} bytes written outside the caller's output buffer"
             fast = sim.timing().fast_path
+            bad_guard = sim.guard_violations()
+        if bad_guard != 0:
+            return f"case {case}: gpusim_debug_guard_violations = {bad_guard} ({note}, opts={opts})"
         same = got.size == want.size and np.array_equal(got, want)
         line = (f"case {case:4d}: N={t.samples_per_epoch:8d} E={t.n_epochs:3d} C={t.max_active():2d} fmt={t.data_format:2d} "
                 f"mode={'float' if t.carrier_mode else 'int  '} {note:20s} opts={opts} via={('host', 'sink', 'device')[how]} "

@@ -1,8 +1,12 @@
 #!/usr/bin/env python3
-"""One short K1+K2 job for ncu: python tools/profile_one.py [fmt] [accum] [epochs] [chunk] [carrier_mode] [pipeline]
+"""One short K1+K2 job for ncu.
 
-pipeline defaults to 2: the synthesis kernel is the build that shares the SM with the next call's chain
-kernel (112 registers) - the one bench.py's back-to-back steps run."""
+    python tools/profile_one.py [fmt] [accum] [epochs] [chunk] [carrier_mode] [pipeline]     synthetic rows
+    python tools/profile_one.py --table <table.npz> [pipeline]                                 a saved EpochTable
+    python tools/profile_one.py --scenario <name> [pipeline]                                   rows recorded from the reference host
+
+Three generate_device calls on resident tables (ncu: --launch-skip past the first ones).  pipeline defaults
+to 0: every call runs its chain kernel and then the synthesis kernel on the same stream."""
 import os
 import sys
 
@@ -11,14 +15,26 @@ sys.path.insert(0, ROOT)
 import torch
 import gps_sdr_sim_b200 as gs
 
-fmt = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-accum = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-E = int(sys.argv[3]) if len(sys.argv) > 3 else 600
-chunk = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-mode = int(sys.argv[5]) if len(sys.argv) > 5 else 0
-pipeline = int(sys.argv[6]) if len(sys.argv) > 6 else 2
-t = gs.synthetic_table(E, 260000, 13, fmt, carrier_mode=mode)
-out = torch.empty(t.n_epochs * t.epoch_bytes, dtype=torch.uint8, device="cuda")
+argv = sys.argv[1:]
+accum, chunk = 1, 0
+if argv and argv[0] == "--table":
+    from gps_sdr_sim_b200.table import EpochTable
+    t = EpochTable.load_npz(argv[1])
+    pipeline = int(argv[2]) if len(argv) > 2 else 0
+elif argv and argv[0] == "--scenario":
+    from gps_sdr_sim_b200 import scenarios
+    t, _ = scenarios.load(argv[1])
+    pipeline = int(argv[2]) if len(argv) > 2 else 0
+else:
+    fmt = int(argv[0]) if len(argv) > 0 else 8
+    accum = int(argv[1]) if len(argv) > 1 else 1
+    E = int(argv[2]) if len(argv) > 2 else 600
+    chunk = int(argv[3]) if len(argv) > 3 else 0
+    mode = int(argv[4]) if len(argv) > 4 else 0
+    pipeline = int(argv[5]) if len(argv) > 5 else 0
+    t = gs.synthetic_table(E, 260000, 13, fmt, carrier_mode=mode)
+E = t.n_epochs
+out = torch.empty(E * t.epoch_bytes, dtype=torch.uint8, device="cuda")
 with gs.GpuSim.for_table(t) as sim:
     sim.set_option("accum", accum)
     sim.set_option("chunk", chunk)
@@ -27,5 +43,5 @@ with gs.GpuSim.for_table(t) as sim:
     for _ in range(3):
         sim.generate_device(0, E, out.data_ptr(), out.numel())
         tm = sim.timing()
-    print(f"pipeline={pipeline} carrier_mode={mode} fmt={fmt} accum={accum} epochs={E} chunk={chunk} k1={tm.chain_ms:.3f} ms k2={tm.synth_ms:.3f} ms "
-          f"{E * 260000 / tm.synth_ms / 1e6:.1f} GS/s")
+    print(f"pipeline={pipeline} carrier_mode={t.carrier_mode} fmt={t.data_format} epochs={E} N={t.samples_per_epoch} "
+          f"k1={tm.chain_ms:.3f} ms k2={tm.synth_ms:.3f} ms {E * t.samples_per_epoch / tm.synth_ms / 1e6:.1f} GS/s")

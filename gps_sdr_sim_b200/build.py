@@ -36,12 +36,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-           *[os.path.join(CSRC, s) for s in SOURCES], "-o", LIB]
+           *[os.path.join(CSRC, s) for s in SOURCES], "-o", LIB + ".tmp"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libgpusim.so")
+    os.replace(LIB + ".tmp", LIB)      # atomically: a snapshot of the tree never sees a half-written library
     return LIB
 
 

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -395,6 +396,18 @@ int gpusim_create(const gpusim_config *cfg, gpusim_ctx **out_ctx)
     if (cfg->carrier_mode != GPUSIM_CARRIER_INT && cfg->carrier_mode != GPUSIM_CARRIER_FLOAT)
         return fail(nullptr, GPUSIM_ERR_ARG, "unknown carrier_mode");
 
+    // GPUSIM_VERBOSE=2: where the start-up time of a context goes (stderr)
+    const char *vb = getenv("GPUSIM_VERBOSE");
+    const bool verbose = vb != nullptr && atoi(vb) >= 2;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!verbose)
+            return;
+        cudaDeviceSynchronize();
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "gpusim_create: %-34s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
     if (ce != cudaSuccess || ndev == 0)
@@ -422,7 +435,10 @@ int gpusim_create(const gpusim_config *cfg, gpusim_ctx **out_ctx)
         }                                                                                          \
     } while (0)
 
+    lap("driver init (cudaGetDeviceCount)");
     GS_CREATE(cudaSetDevice(cfg->device));
+    GS_CREATE(cudaFree(nullptr));
+    lap("context (cudaSetDevice + cudaFree(0))");
     GS_CREATE(cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));
     GS_CREATE(cudaStreamCreateWithFlags(&ctx->s_chain, cudaStreamNonBlocking));
     GS_CREATE(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
@@ -468,14 +484,17 @@ int gpusim_create(const gpusim_config *cfg, gpusim_ctx **out_ctx)
         GS_CREATE(cudaMemcpy(ctx->d_negw, negw.data(), negw.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
 
+    lap("streams, events, constant tables");
     const size_t rows = (size_t)cfg->max_batch_epochs * kMaxChan;
     GS_CREATE(dev_alloc(ctx, &ctx->d_rows, rows * sizeof(DevRow)));
     GS_CREATE(dev_alloc(ctx, &ctx->d_nch, (size_t)cfg->max_batch_epochs));
     GS_CREATE(dev_alloc(ctx, &ctx->d_x0, rows * sizeof(double)));
+    lap("device row buffers");
     GS_CREATE(cudaMallocHost(&ctx->h_rows, rows * sizeof(DevRow)));
     GS_CREATE(cudaMallocHost(&ctx->h_nch, (size_t)cfg->max_batch_epochs));
     GS_CREATE(cudaMallocHost(&ctx->h_x0, rows * sizeof(double)));
 
+    lap("page-locked row buffers");
     // checkpoints: 10 (18 with a double carrier) bytes per (row, chunk); raise the minimum chunk until
     // they fit the budget
     const bool cf = cfg->carrier_mode == GPUSIM_CARRIER_FLOAT;
@@ -498,6 +517,7 @@ int gpusim_create(const gpusim_config *cfg, gpusim_ctx **out_ctx)
     }
     GS_CREATE(cudaMemset(ctx->d_work, 0, 64));
     GS_CREATE(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
+    lap("checkpoint buffers");
 #undef GS_CREATE
 
     *out_ctx = ctx;

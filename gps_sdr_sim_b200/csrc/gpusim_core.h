@@ -417,6 +417,45 @@ GS_HD bool warp_any(unsigned mask, bool pred) // kept for callers that vote; on 
 //     room / |delta| and the floor never overshoots: no verification, no fix-up.  When it falls
 //     short by a step (probability ~2^(2s-50) per jump) that step is simply taken as a real addition.
 //     The floor is the low word of RD(room * r + 2^52): no conversion instructions on the chain.
+// The constants of one binade [2^e, 2^(e+1)) for a given step d: everything in the jump that does not
+// depend on x.  The walk visits the binades in order (a rising chain leaves binade e into e+1), so the
+// constants of the NEXT binade are computed while the current trip's dependent chain (subtract, multiply,
+// floor, fused multiply-add, real add: ~6 FP64 latencies) is in flight - the walk is latency bound, its
+// issue slots are idle.
+struct BinadeConsts {
+    int bex;      // biased exponent these constants belong to
+    bool ok;      // a jump is possible in this binade (|d| < c/2, k < 2^31, d != 0)
+    double delta; // RN_ulp(d): what one step adds (0 when !ok)
+    double lim;   // furthest landing: pred(min(2c, M)) rising, succ(c) falling
+    double r;     // (1/|d|) * (1 - 2^(s-50))
+};
+template <int kSign>
+GS_HD BinadeConsts binade_consts(const int bex, const double d, const int bex_d, const uint64_t mbits, const double rd)
+{
+    BinadeConsts k;
+    const int shift = bex - bex_d;
+    k.bex = bex;
+    k.ok = shift >= 2 && shift <= 30 && rd != 0.0;
+    k.delta = 0.0;
+    k.lim = 0.0;
+    k.r = 0.0;
+    if (k.ok) {
+        const uint64_t cb = (uint64_t)bex << 52; // c = 2^e
+        if (kSign > 0) {
+            const double c = dfrombits(cb);
+            k.delta = dadd(dadd(c, d), -c);
+            const uint64_t c2b = cb + (1ull << 52);                // 2c
+            k.lim = dfrombits((c2b > mbits ? mbits : c2b) - 1);   // pred(min(2c, M))
+        } else {
+            const double c15 = dfrombits(cb | (1ull << 51)); // 1.5c
+            k.delta = dadd(dadd(c15, d), -c15);              // negative
+            k.lim = dfrombits(cb + 1);                       // succ(c)
+        }
+        k.r = dfma(-rd, dfrombits((uint64_t)(1023 - 50 + shift) << 52), rd);
+    }
+    return k;
+}
+
 template <int kSign = 0, class Emit>
 GS_HD double phase_chain(double x, const double d, const double M, const int n_end, const int every,
                          Emit emit, const unsigned mask = 0xffffffffu)
@@ -425,54 +464,47 @@ GS_HD double phase_chain(double x, const double d, const double M, const int n_e
     if (kSign == 0)
         return d < 0.0 ? phase_chain<-1>(x, d, M, n_end, every, emit) : phase_chain<1>(x, d, M, n_end, every, emit);
     constexpr bool neg = kSign < 0;
+    constexpr int kS = kSign == 0 ? 1 : kSign;
     const uint64_t db = dbits(neg ? -d : d);
     const int bex_d = (int)(db >> 52); // biased exponent of |d| (d is finite and normal or zero)
     const uint64_t dm = db & 0xfffffffffffffull;
-    const int tie_s = dm ? ctz64(dm) + 1 : 0;
-    const double rd = db ? 1.0 / (neg ? -d : d) : 0.0; // d == 0: never used (every step is a real "x += 0")
+    const int tie_bex = dm ? bex_d + ctz64(dm) + 1 : -1; // the one binade in which d is an exact half-ulp tie
+    const double rd = db ? 1.0 / (neg ? -d : d) : 0.0;   // d == 0: no jumps, every step is a real "x += 0"
     const uint64_t mbits = dbits(M);
     int n = 0, next = every, j = 1, wraps = 0;
 
     emit(0, x, 0);
+    BinadeConsts cur = binade_consts<kS>((int)(dbits(x) >> 52), d, bex_d, mbits, rd);
     while (n < n_end) {
         const uint64_t xb = dbits(x);
         const int bex = (int)(xb >> 52); // x is in [0, M): sign bit clear
-        const int shift = bex - bex_d;
-        // jump inside this binade: needs |d| < c/2 (anchor + d stays in the binade), k below 2^31, no odd tie
-        if (shift >= 2 && shift <= 30 && !(shift == tie_s && (xb & 1u)) && db != 0) {
-            const uint64_t cb = (uint64_t)bex << 52; // c = 2^e
-            double delta, room;
-            if (!neg) {
-                const double c = dfrombits(cb);
-                delta = dadd(dadd(c, d), -c);
-                const uint64_t c2b = cb + (1ull << 52);                    // 2c
-                const double top = dfrombits((c2b > mbits ? mbits : c2b) - 1); // pred(min(2c, M))
-                room = dadd(top, -x);
-            } else {
-                const double c15 = dfrombits(cb | (1ull << 51)); // 1.5c
-                delta = dadd(dadd(c15, d), -c15);                // negative
-                room = dadd(x, -dfrombits(cb + 1));              // down to succ(c); -u when x == c
-            }
-            const double r = dfma(-rd, dfrombits((uint64_t)(1023 - 50 + shift) << 52), rd);
-            const double m1 = dadd_down(dmul(room, r), 4503599627370496.0); // 2^52 + floor(room * r)
-            int k = (int)(uint32_t)dbits(m1);
-            double kf = dadd(m1, -4503599627370496.0);
-            if (GS_UNLIKELY(k > n_end - n)) {
-                k = n_end - n;
-                kf = (double)k;
-            }
-            if (k > 0) {
-                // checkpoints that fall inside the jump
-                while (GS_UNLIKELY(next - n <= k)) {
-                    emit(j++, dfma((double)(next - n), delta, x), wraps);
-                    next += every;
-                }
-                x = dfma(kf, delta, x);
-                n += k;
-                if (n >= n_end)
-                    break;
-            }
+        if (GS_UNLIKELY(bex != cur.bex)) // after the wrap, in the binades too small to jump in, or when a jump fell short
+            cur = binade_consts<kS>(bex, d, bex_d, mbits, rd);
+        // the binade the real step of this trip will (almost always) land in
+        const BinadeConsts nxt = binade_consts<kS>(neg ? bex - 1 : bex + 1, d, bex_d, mbits, rd);
+        // jump inside this binade; an exact tie from an odd significand takes its real step first
+        const bool go = cur.ok && !(bex == tie_bex && (xb & 1u));
+        const double room = neg ? dadd(x, -cur.lim) : dadd(cur.lim, -x); // falling: -ulp when x == c
+        const double m1 = dadd_down(dmul(room, cur.r), 4503599627370496.0); // 2^52 + floor(room * r)
+        int k = (int)(uint32_t)dbits(m1);
+        double kf = dadd(m1, -4503599627370496.0);
+        if (!go || k < 0) {
+            k = 0;
+            kf = 0.0;
         }
+        if (GS_UNLIKELY(k > n_end - n)) {
+            k = n_end - n;
+            kf = (double)k;
+        }
+        // checkpoints that fall inside the jump
+        while (GS_UNLIKELY(k > 0 && next - n <= k)) {
+            emit(j++, dfma((double)(next - n), cur.delta, x), wraps);
+            next += every;
+        }
+        x = dfma(kf, cur.delta, x); // k == 0: x + 0*delta = x
+        n += k;
+        if (GS_UNLIKELY(n >= n_end))
+            break;
         // one genuine step: crosses the binade edge, wraps, or walks the binades too small to jump in
         x = dadd(x, d);
         if (!neg) { // a rising chain leaves [0, M) at the top only, a falling one at the bottom
@@ -489,6 +521,7 @@ GS_HD double phase_chain(double x, const double d, const double M, const int n_e
             emit(j++, x, wraps);
             next += every;
         }
+        cur = nxt;
     }
     return x;
 }

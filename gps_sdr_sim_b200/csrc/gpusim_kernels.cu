@@ -42,7 +42,7 @@ static cudaError_t set_attr_once(cudaFuncAttribute attr, int value)
 // K1
 // ------------------------------------------------------------------------------------
 template <bool kReplay>
-__global__ void __maxnreg__(32) k1_chain(DeviceJob job)
+__global__ void __launch_bounds__(32) k1_chain(DeviceJob job)
 {
     // One warp = ONE channel slot over 32 consecutive epochs.  The host re-derives the code phase
     // from the pseudorange every epoch, but the signal is continuous, so the same satellite starts

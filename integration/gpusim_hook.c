@@ -171,6 +171,10 @@ struct gpusim_hook
 	int failed;      /* a worker or the writer hit an error: everybody stops, the MAIN thread reports and exits */
 	char fail_msg[600];
 	long epochs_written; /* epochs delivered to the output file so far (what a failure report states) */
+	gpusim_config cfg;   /* what every worker creates its context with */
+	size_t epoch_bytes;  /* gpssim.c:2276/:2283/:2287 */
+	int slots_ready;     /* page-locked ring buffers allocated (several GPUs; done by worker 0 once CUDA is up) */
+	double t_ctx;        /* wall clock [s] the slowest worker spent creating its context */
 };
 
 static double now_s(void)
@@ -526,6 +530,42 @@ static void *worker_main(void *arg)
 {
 	worker_t *w = (worker_t *)arg;
 	gpusim_hook *h = w->h;
+	/* CUDA start-up (driver initialisation + context: several hundred ms) happens HERE, on the worker, while
+	 * the main thread is already reading the RINEX file and filling rows. */
+	{
+		const double t0 = now_s();
+		gpusim_config cfg = h->cfg;
+		int rc;
+		cfg.device = w->device;
+		rc = gpusim_create(&cfg, &w->ctx);
+		if (rc != GPUSIM_OK)
+		{
+			pipeline_fail(h, "Failed to initialise the GPU sample generator", gpusim_last_error(NULL));
+			return NULL;
+		}
+		if (h->ndev > 1 && w->index == 0)
+		{
+			int d;
+			for (d = 0; d < h->nslots; d++)
+			{
+				h->slots[d].out = gpusim_host_alloc((size_t)h->cap_max * h->epoch_bytes);
+				if (h->slots[d].out == NULL)
+				{
+					pipeline_fail(h, "Failed to allocate page-locked output buffers", NULL);
+					return NULL;
+				}
+			}
+		}
+		pthread_mutex_lock(&h->mu);
+		if (h->ndev == 1 || w->index == 0)
+			h->slots_ready = 1;
+		if (now_s() - t0 > h->t_ctx)
+			h->t_ctx = now_s() - t0;
+		pthread_cond_broadcast(&h->cv);
+		while (!h->slots_ready && !h->failed)
+			pthread_cond_wait(&h->cv, &h->mu);
+		pthread_mutex_unlock(&h->mu);
+	}
 	for (;;)
 	{
 		slot_t *s;
@@ -550,7 +590,7 @@ static void *worker_main(void *arg)
 		if (h->ndev == 1) /* one GPU: this thread is also the (ordered) writer, from the library's staging buffers */
 			rc = gpusim_generate_epochs_to_sink(w->ctx, &t, sink_fwrite, h);
 		else
-			rc = gpusim_generate_epochs(w->ctx, &t, s->out, (size_t)h->cap_max * gpusim_epoch_bytes(w->ctx));
+			rc = gpusim_generate_epochs(w->ctx, &t, s->out, (size_t)h->cap_max * h->epoch_bytes);
 		if (rc != GPUSIM_OK)
 		{
 			pipeline_fail(h, rc == GPUSIM_ERR_SINK ? "Failed to write the output file" : "GPU sample generation failed",
@@ -571,7 +611,7 @@ static void *worker_main(void *arg)
 static void *writer_main(void *arg)
 {
 	gpusim_hook *h = (gpusim_hook *)arg;
-	const size_t eb = gpusim_epoch_bytes(h->workers[0].ctx);
+	const size_t eb = h->epoch_bytes;
 	long seq;
 	for (seq = 0;; seq++)
 	{
@@ -728,7 +768,7 @@ gpusim_hook *gpusim_hook_open(int iq_buff_size, double delt, int data_format, FI
 	if (!h->dryrun)
 	{
 		gpusim_config cfg;
-		int rc, d;
+		int d;
 		memset(&cfg, 0, sizeof(cfg));
 		cfg.abi_version = GPUSIM_ABI_VERSION;
 		cfg.samples_per_epoch = iq_buff_size;
@@ -746,12 +786,10 @@ gpusim_hook *gpusim_hook_open(int iq_buff_size, double delt, int data_format, FI
 		h->slots = calloc((size_t)h->nslots, sizeof(slot_t));
 		if (h->slots == NULL)
 			die("gpusim hook out of memory", NULL);
+		h->cfg = cfg;
+		h->epoch_bytes = data_format == 16 ? (size_t)4 * iq_buff_size : data_format == 8 ? (size_t)2 * iq_buff_size : (size_t)(iq_buff_size / 4);
 		for (d = 0; d < h->ndev; d++)
 		{
-			cfg.device = h->workers[d].device;
-			rc = gpusim_create(&cfg, &h->workers[d].ctx);
-			if (rc != GPUSIM_OK)
-				die("Failed to initialise the GPU sample generator", gpusim_last_error(NULL));
 			h->workers[d].h = h;
 			h->workers[d].index = d;
 		}
@@ -759,12 +797,6 @@ gpusim_hook *gpusim_hook_open(int iq_buff_size, double delt, int data_format, FI
 		{
 			cols_reserve(&h->slots[d].rows, batch);
 			h->slots[d].rows.cap = batch;
-			if (h->ndev > 1)
-			{
-				h->slots[d].out = gpusim_host_alloc((size_t)batch * gpusim_epoch_bytes(h->workers[0].ctx));
-				if (h->slots[d].out == NULL)
-					die("Failed to allocate page-locked output buffers", NULL);
-			}
 		}
 		for (d = 0; d < h->ndev; d++)
 			pthread_create(&h->workers[d].thread, NULL, worker_main, &h->workers[d]);
@@ -879,7 +911,8 @@ void gpusim_hook_close(gpusim_hook *h)
 		pipeline_join(h);
 		pipeline_check(h); /* reports and exits if anything failed */
 		for (d = 0; d < h->ndev; d++)
-			gpusim_destroy(h->workers[d].ctx);
+			if (h->workers[d].ctx != NULL)
+				gpusim_destroy(h->workers[d].ctx);
 		for (d = 0; d < h->nslots; d++)
 		{
 			cols_free(&h->slots[d].rows);
@@ -891,9 +924,9 @@ void gpusim_hook_close(gpusim_hook *h)
 	pool_stop(&h->pool);
 	if ((v = getenv("GPUSIM_VERBOSE")) != NULL && atoi(v) != 0)
 		fprintf(stderr, "\ngpusim hook: %ld epochs, %d host threads, range look-ahead: %ld windows, %ld hits, %ld direct calls\n"
-		                "gpusim hook: %.3f s from open to close; main thread: %.3f s range windows, %.3f s carrier chains, %.3f s waiting for the GPU pipeline; batches up to %d epochs\n",
+		                "gpusim hook: %.3f s from open to close (context creation on the worker: %.3f s, overlapped with the host's row pre-pass); main thread: %.3f s range windows, %.3f s carrier chains, %.3f s waiting for the GPU pipeline; batches up to %d epochs\n",
 		        h->epochs_done, h->host_threads, h->ra.windows, h->ra.hits, h->ra.direct,
-		        now_s() - h->t_open, h->t_ranges, h->t_chains, h->t_wait, h->cap_max);
+		        now_s() - h->t_open, h->t_ctx, h->t_ranges, h->t_chains, h->t_wait, h->cap_max);
 	if (h->dump_path != NULL)
 		write_dump(h);
 	free(h->ra.rho);

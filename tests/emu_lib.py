@@ -16,12 +16,15 @@ _lib = None
 TUNED32, TUNED16, GENERIC = 0, 1, 2
 
 
-def build() -> str:
-    so = os.path.join(EMU_DIR, "libgpusim_emu.so")
+def build(sanitized: bool = False) -> str:
+    """sanitized: the same code with AddressSanitizer + UndefinedBehaviorSanitizer (tests/test_emu_sanitized.py
+    runs it in a subprocess with the ASan runtime preloaded)."""
+    so = os.path.join(EMU_DIR, "libgpusim_emu_asan.so" if sanitized else "libgpusim_emu.so")
     deps = [os.path.join(EMU_DIR, "emu.cpp"), os.path.join(CSRC, "gpusim_core.h"),
             os.path.join(CSRC, "gpusim_tables.cpp"), os.path.join(CSRC, "gpusim_tables.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall",
+        flags = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all"] if sanitized else ["-O2"]
+        subprocess.run(["g++", *flags, "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall",
                         "-Wno-unknown-pragmas", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
                         deps[0], deps[2], "-o", so], check=True, capture_output=True)
     return so
@@ -30,7 +33,7 @@ def build() -> str:
 def lib() -> ctypes.CDLL:
     global _lib
     if _lib is None:
-        _lib = ctypes.CDLL(build())
+        _lib = ctypes.CDLL(build(sanitized=os.environ.get("GPUSIM_EMU_SANITIZED") == "1"))
         _lib.emu_generate.restype = ctypes.c_int
         _lib.emu_generate.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int,
                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]

@@ -39,6 +39,11 @@ __global__ void __launch_bounds__(512, 1) probe(uint64_t *sink, double dseed, in
             if (MODE == 13) { w[i] = w[i] ^ (it & 0x80000000); }                                  // LOP3
             if (MODE == 14) { w[i] = (uint32_t)w[i] >> 23; }                                        // SHF
             if (MODE == 15) { w[i] = w[i] + iseed; }                                                // IADD
+            if (MODE == 17) { long long r; asm volatile("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(iseed), "n"(0x50000), "l"((long long)u[i])); u[i] = r; } // IMAD.WIDE, immediate multiplier
+            if (MODE == 18) { long long r; asm volatile("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(w[i]), "n"(0x50000), "l"((long long)gg)); uint32_t a2; asm volatile("lop3.b32 %0, %1, 0xff80, %2, 0xea;" : "=r"(a2) : "r"((uint32_t)(r >> 32)), "r"(lane * 8)); w[i] = (int32_t)a2; } // IMAD.WIDE + LOP3 address pair
+            if (MODE == 19) { int32_t v; asm volatile("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"((uint32_t)(w[i] & 0x3ff))); w[i] = v + it; }  // dependent LDS.S8, warp-uniform-ish address
+            if (MODE == 20) { u[i] = sm[((u[i] >> 9) & 0x1ff0) | (lane & 15)]; asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(u[(i + 1) % UNROLL]) : "l"(u[i]), "l"(gg)); } // LDS.64 + FFMA2
+            if (MODE == 21) { asm volatile("{.reg .b16 h0, h1; mov.b32 {h0, h1}, %1; fma.rn.f32.f16 %0, h0, h1, %0;}" : "+f"(*(float *)&w[i]) : "r"(iseed)); } // mixed f32 += f16*f16
             if (MODE == 16) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x78;" : "+r"(w[i]) : "r"(iseed), "r"(it)); w[i] = w[i] * 128 + iseed; } // LOP3 + IMAD pair (two pipes)
         }
     }
@@ -87,5 +92,10 @@ int main()
     run<14>("SHF", sink, sms);
     run<15>("IADD", sink, sms);
     run<16>("LOP3+IMAD pair", sink, sms);
+    run<17>("IMAD.WIDE imm multiplier", sink, sms);
+    run<18>("IMAD.WIDE imm + LOP3 addr", sink, sms);
+    run<19>("LDS.S8 dependent", sink, sms);
+    run<20>("LDS.64 + FFMA2", sink, sms);
+    run<21>("FMA f32 += f16*f16 (mixed)", sink, sms);
     return 0;
 }

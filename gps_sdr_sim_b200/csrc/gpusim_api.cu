@@ -57,6 +57,8 @@ struct gpusim_ctx {
     int n_uploaded = 0;
     bool needs_generic = false;
     double d_max = 0.0;
+    double d_min = 0.0;   // smallest f_code*delt of the uploaded table (low-chip-rate path, synth_lin)
+    int lin_nb = 0;        // > 0: the uploaded table qualifies for synth_lin with this many chip boundaries per run
 
     // checkpoints, sized for min_chunk
     double *d_ck_x[2] = {nullptr, nullptr};
@@ -72,7 +74,7 @@ struct gpusim_ctx {
     uint8_t *h_stage[2] = {nullptr, nullptr};
 
     // options
-    int opt_chunk = 0, opt_force_generic = 0, opt_force_slow = 0, opt_chain_replay = 0, opt_accum = 1, opt_layout = 0, opt_pipeline = 1, opt_float_geom = 0, opt_lean = 1;
+    int opt_chunk = 0, opt_force_generic = 0, opt_force_slow = 0, opt_chain_replay = 0, opt_accum = 1, opt_layout = 0, opt_pipeline = 1, opt_float_geom = 0, opt_lean = 1, opt_lowrate = 1;
     int opt_direct_first_mb = 16, opt_direct_mb = 64; // sub-batch sizes when copying straight into the caller's buffer
 
     gpusim_timing timing{};
@@ -233,6 +235,12 @@ SynthKernel plan_job(gpusim_ctx *ctx, int first, int n, uint8_t *out_dev, Device
     job.force_wrap_path = ctx->opt_force_slow;
     job.float_narrow = ctx->opt_float_geom == 1 ? 1 : 0;
     job.lean = ctx->opt_lean;
+    job.lin_nb = 0;
+    job.lin_rinv = 0.0;
+    if (which == SynthKernel::Tuned32 && !job.carrier_float && job.accum == 1 && job.lean && ctx->opt_lowrate && ctx->lin_nb > 0) {
+        job.lin_nb = ctx->lin_nb;
+        job.lin_rinv = 2.0 / (ctx->d_min + ctx->d_max);
+    }
 
     return which;
 }
@@ -244,12 +252,10 @@ DeviceJob sub_job(const gpusim_ctx *ctx, const DeviceJob &whole, int first, int 
     job.rows = whole.rows + (size_t)first * kMaxChan;
     job.nch = whole.nch + first;
     job.x0 = whole.x0 + (size_t)first * kMaxChan;
-    job.ck_x = whole.ck_x + (size_t)first * kMaxChan * whole.kc;
-    job.ck_w = whole.ck_w + (size_t)first * kMaxChan * whole.kc;
+    job.ck_e0 = whole.ck_e0 + first;
     if (whole.carrier_float) {
         job.dc = whole.dc + (size_t)first * kMaxChan;
         job.cph0 = whole.cph0 + (size_t)first * kMaxChan;
-        job.ck_c = whole.ck_c + (size_t)first * kMaxChan * whole.kc;
     }
     job.out = out_dev;
     job.n_epochs = n;
@@ -501,7 +507,7 @@ int gpusim_create(const gpusim_config *cfg, gpusim_ctx **out_ctx)
     ctx->min_chunk = 128;
     while (rows * (size_t)kc_for(N, ctx->min_chunk) * (cf ? 18 : 10) > kCheckpointBudget && ctx->min_chunk < (1 << 20))
         ctx->min_chunk *= 2;
-    const size_t cks = rows * (size_t)kc_for(N, ctx->min_chunk);
+    const size_t cks = ck_elems(cfg->max_batch_epochs, kc_for(N, ctx->min_chunk));
     for (int i = 0; i < 2; i++) {
         GS_CREATE(dev_alloc(ctx, &ctx->d_ck_x[i], cks * sizeof(double)));
         GS_CREATE(dev_alloc(ctx, &ctx->d_ck_w[i], cks * sizeof(uint16_t)));
@@ -537,6 +543,7 @@ int gpusim_set_option(gpusim_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "pipeline")) ctx->opt_pipeline = (int)value;
     else if (!strcmp(key, "float_geom")) ctx->opt_float_geom = (int)value;
     else if (!strcmp(key, "lean")) ctx->opt_lean = (int)value;
+    else if (!strcmp(key, "lowrate")) ctx->opt_lowrate = (int)value;
     else if (!strcmp(key, "direct_first_mb")) ctx->opt_direct_first_mb = (int)std::max<int64_t>(1, value);
     else if (!strcmp(key, "direct_mb")) ctx->opt_direct_mb = (int)std::max<int64_t>(1, value);
     else return fail(ctx, GPUSIM_ERR_ARG, "unknown option '%s'", key);
@@ -567,6 +574,8 @@ int gpusim_upload_table(gpusim_ctx *ctx, const gpusim_epoch_table *t)
     const double delt = ctx->cfg.delt;
     ctx->needs_generic = false;
     ctx->d_max = 0.0;
+    ctx->d_min = (double)kCaLen;
+    ctx->lin_nb = 0;
     for (int e = 0; e < t->n_epochs; e++) {
         int nc = 0;
         for (int i = 0; i < kMaxChan; i++) {
@@ -603,6 +612,9 @@ int gpusim_upload_table(gpusim_ctx *ctx, const gpusim_epoch_table *t)
                 ctx->needs_generic = true;
             }
             ctx->d_max = std::max(ctx->d_max, (double)d);
+            ctx->d_min = std::min(ctx->d_min, (double)d);
+            if (chain_tie_binade(d) >= 5 && chain_tie_binade(d) <= 9)
+                o.flags |= kRowTieInLinRange;
             ctx->h_x0[(size_t)e * kMaxChan + nc] = x0;
             nc++;
         }
@@ -615,6 +627,16 @@ int gpusim_upload_table(gpusim_ctx *ctx, const gpusim_epoch_table *t)
             }
         }
         ctx->h_nch[e] = (uint8_t)nc;
+    }
+    // Low chip rates (synth_lin): at most 2 or 4 chip boundaries per run of 32 samples, and one job-wide 1/d
+    // good to 1e-3 samples over a whole run.  Rows whose step is an exact half-ulp tie in one of the binades
+    // the linear model is used in get a wrap threshold of 0: they always take the exact per-sample loop.
+    if (!cf && t->n_epochs > 0 && ctx->d_max > 0.0 && 32.0 * ctx->d_max < 4.0 &&
+        5.0 * (ctx->d_max - ctx->d_min) < 0.25 * ctx->d_min * ctx->d_min) { // quotient estimate off by < 0.25 samples
+        ctx->lin_nb = 32.0 * ctx->d_max < 2.0 ? 2 : 4;
+        for (size_t r = 0; r < (size_t)t->n_epochs * kMaxChan; r++)
+            if (ctx->h_rows[r].flags & kRowTieInLinRange)
+                ctx->h_rows[r].cthr_prn &= (uint16_t)~kCthrMask;
     }
     const size_t rows = (size_t)t->n_epochs * kMaxChan;
     if (rows) {

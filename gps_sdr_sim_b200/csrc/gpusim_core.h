@@ -60,6 +60,7 @@ constexpr int kCaPrns = 33;          // index by prn 0..32 (0 unused)
 constexpr int kCaWin64 = 34;         // per PRN: 64-bit windows {word i+1, word i}, i = 0..33 (one LDS.64 per chip window)
 constexpr int kCaWinBytes = kCaWin64 * 8;
 constexpr uint32_t kCthrMask = 0x3ffu;
+constexpr double kCarrMod = 512.0;  // FLOAT_CARR_PHASE hosts: the device keeps 512 * carr_phase
 
 // ---- exact IEEE-754 double steps (never contracted into FMA) -----------------------
 // Host: the sum / product must be rounded to double on its own, never fused with a neighbouring
@@ -206,6 +207,7 @@ GS_HD int row_cthr(const DevRow &r) { return (int)(r.cthr_prn & kCthrMask); }
 GS_HD int row_prn(const DevRow &r) { return (int)(r.cthr_prn >> 10); }
 
 constexpr uint32_t kRowNeedsGeneric = 1u;
+constexpr uint32_t kRowTieInLinRange = 2u; // f_code*delt is an exact half-ulp tie in one of the binades [2^5, 2^10) (synth_lin)
 constexpr int kTunedMaxGain = 255; // 16 ch * 250 * 255 + 64 < 2^20: the accumulator fields below hold it
 
 // ---- accumulator policies of the tuned kernel -----------------------------------------
@@ -373,6 +375,14 @@ GS_HD int ctz64(uint64_t v) // v != 0
     return __builtin_ctzll(v);
 #endif
 }
+// unbiased exponent e of the one binade [2^e, 2^(e+1)) in which the step d > 0 is an exact half-ulp tie
+// (x + d halfway between two doubles for every x of that binade), or a large negative number if there is none
+GS_HD int chain_tie_binade(double d)
+{
+    const uint64_t db = dbits(d);
+    const uint64_t dm = db & 0xfffffffffffffull;
+    return dm ? (int)(db >> 52) + ctz64(dm) + 1 - 1023 : -100000;
+}
 GS_HD bool warp_any(unsigned mask, bool pred) // kept for callers that vote; on the host a "warp" is one thread
 {
 #ifdef __CUDA_ARCH__
@@ -526,13 +536,140 @@ GS_HD double phase_chain(double x, const double d, const double M, const int n_e
     return x;
 }
 
+// ---- the same walk with the binade constants tabulated up front ------------------------------------
+// phase_chain() derives the constants of a binade whenever the chain enters it - on a GPU that is most of
+// the instructions of a trip (ncu, round 2: ~130 SASS instructions per trip, 6 cycles each on a lone
+// in-order warp).  The constants depend on d only, and a chain below M <= 1024 only ever visits the binades
+// [2^-4, 2^10): phase_chain_tab() tabulates them once per chain (14 entries x {delta, lim, r}, shared
+// memory on the device, the stack on the host) and a trip is then: three loads, lim - x, one round-down
+// fused multiply-add (the floor of the jump count), the jump itself (one FMA) and the real step - the
+// arithmetic, and with it every value, is the one phase_chain() documents.  Entry 0 stands for everything
+// below 2^-3 and never jumps (r = 0 gives k = 0): those few steps are real additions.
+constexpr int kChainTabLo = 1023 - 4; // biased exponent of table entry 0
+constexpr int kChainTabN = 14;        // entries 1..13: binades 2^-3 .. 2^9
+struct ChainTabHost {                 // host / emulation storage; the device uses shared memory (gpusim_kernels.cu)
+    double v[3][kChainTabN];
+    GS_HD void set(int b, double delta, double lim, double r)
+    {
+        v[0][b] = delta;
+        v[1][b] = lim;
+        v[2][b] = r;
+    }
+    GS_HD double delta(int b) const { return v[0][b]; }
+    GS_HD double lim(int b) const { return v[1][b]; }
+    GS_HD double r(int b) const { return v[2][b]; }
+};
+GS_HD double dfma_down(double a, double b, double c) // the exact a*b + c rounded towards -infinity
+{
+#ifdef __CUDA_ARCH__
+    return __fma_rd(a, b, c);
+#else
+    // host: only called with c = 2^52 and |a*b| < 2^31: the rounded-down sum is 2^52 + floor(a*b); a*b is
+    // evaluated exactly as a double-double (fma gives the rounding error of the product)
+    const double p = a * b;
+    const double e = __builtin_fma(a, b, -p); // a*b = p + e exactly
+    double f = __builtin_floor(p);
+    if (f == p && e < 0.0)
+        f -= 1.0; // the exact product lies just below the integer p
+    return c + f;
+#endif
+}
+
+GS_HD double int_as_double_exact(uint32_t k) // (double)k for 0 <= k < 2^32 without a conversion instruction
+{
+    return dadd(dfrombits(0x4330000000000000ull | (uint64_t)k), -4503599627370496.0);
+}
+
+template <int kSign, class Tab, class Emit>
+GS_HD double phase_chain_tab(double x, const double d, const double M, const int n_end, const int every, Tab &tab,
+                             Emit emit)
+{
+    static_assert(kSign == 1 || kSign == -1, "the caller resolves the sign of d");
+    constexpr bool neg = kSign < 0;
+    const uint64_t db = dbits(neg ? -d : d);
+    const int bex_d = (int)(db >> 52);
+    const uint64_t dm = db & 0xfffffffffffffull;
+    const int tie_bi = dm ? bex_d + ctz64(dm) + 1 - kChainTabLo : -1; // table index of the one binade where d is a tie
+    const double rd = db ? 1.0 / (neg ? -d : d) : 0.0;
+    const uint64_t mbits = dbits(M);
+    tab.set(0, 0.0, 0.0, 0.0);
+    for (int b = 1; b < kChainTabN; b++) {
+        const BinadeConsts k = binade_consts<kSign>(kChainTabLo + b, d, bex_d, mbits, rd);
+        tab.set(b, k.delta, k.lim, k.ok ? k.r : 0.0);
+    }
+    // The walk is driven by the checkpoints, not the other way round.  State: x = the value after n steps and
+    // the SEGMENT that starts there - k more steps of delta each that stay inside x's binade.  A checkpoint
+    // inside the segment is x + (target - n) * delta (any count up to k is as exact as k itself); only a target
+    // beyond it makes the chain take the segment, one genuine step (the one that crosses the binade edge, wraps,
+    // or walks the untabulated binades) and open the next segment.  On the device every lane of a warp thus
+    // emits checkpoint j at the same point of the program - one coalesced store per warp - whatever the number
+    // of trips each lane needed to get there, and no trip is spent on stopping at a checkpoint.
+    int n = 0, wraps = 0, k = 0;
+    double delta = 0.0;
+    auto open_segment = [&]() {
+        const uint64_t xb = dbits(x);
+        int bi = (int)(xb >> 52) - kChainTabLo; // x in [0, M), M <= 1024: bi <= 13
+        bi = bi < 0 ? 0 : bi;
+        const double room = neg ? dadd(x, -tab.lim(bi)) : dadd(tab.lim(bi), -x);
+        const double m1 = dfma_down(room, tab.r(bi), 4503599627370496.0); // 2^52 + floor(room * r)
+        k = (int)(uint32_t)dbits(m1);
+        // no jump: an exact tie from an odd significand takes its real step first; a falling chain sitting on
+        // the binade's lower edge has room < 0; the untabulated binades have r = 0
+        if ((bi == tie_bi && (xb & 1u)) || (neg && k < 0))
+            k = 0;
+        delta = tab.delta(bi);
+    };
+    auto value_at = [&](int target) { // target - n in [0, k]
+        return dfma(int_as_double_exact((uint32_t)(target - n)), delta, x);
+    };
+    open_segment();
+    int j = 0;
+    for (int target = 0;;) {
+        while (target - n > k) {
+            x = dfma(int_as_double_exact((uint32_t)k), delta, x);
+            x = dadd(x, d);
+            if (!neg) {
+                if (x >= M) {
+                    x = dadd(x, -M);
+                    wraps++;
+                }
+            } else if (x < 0.0) {
+                x = dadd(x, M);
+                wraps++;
+            }
+            n += k + 1;
+            open_segment();
+        }
+        if (target == n_end && j > 0 && (n_end % every) != 0)
+            break; // the final advance to n_end is not a checkpoint
+        emit(j++, value_at(target), wraps);
+        if (target == n_end)
+            break;
+        target = (n_end - target < every) ? n_end : target + every;
+    }
+    return value_at(n_end);
+}
+
 // K1's use: code-phase checkpoints at sample indices j*every, j = 0 .. ceil(n_total/every)-1.
-template <class Emit>
-GS_HD void code_chain(double x, const double d, const int n_total, const int every, Emit emit,
-                      const unsigned mask = 0xffffffffu)
+template <class Tab, class Emit>
+GS_HD void code_chain(double x, const double d, const int n_total, const int every, Tab &tab, Emit emit)
 {
     const int last = ((n_total - 1) / every) * every; // sample index of the last checkpoint
-    phase_chain<1>(x, d, (double)kCaLen, last, every, emit, mask); // f_code*delt > 0
+    phase_chain_tab<1>(x, d, (double)kCaLen, last, every, tab, emit); // f_code*delt > 0
+}
+template <class Emit>
+GS_HD void code_chain(double x, const double d, const int n_total, const int every, Emit emit)
+{
+    ChainTabHost tab;
+    code_chain(x, d, n_total, every, tab, emit);
+}
+// carrier chain of a FLOAT_CARR_PHASE host (512 * carr_phase, either sign of the step): checkpoints as above,
+// returns the phase after n_end steps
+template <class Tab, class Emit>
+GS_HD double carrier_chain(double x, const double dc, const int n_end, const int every, Tab &tab, Emit emit)
+{
+    return dc < 0.0 ? phase_chain_tab<-1>(x, dc, kCarrMod, n_end, every, tab, emit)
+                    : phase_chain_tab<1>(x, dc, kCarrMod, n_end, every, tab, emit);
 }
 
 // Plain replay of the same chain (N dependent adds); kept as the in-tree cross-check of
@@ -658,6 +795,77 @@ GS_HD void synth_fast_g(typename A::acc_t (&acc)[S], double &x, uint32_t &phs, c
     }
 }
 
+// ---- low chip rates: the chips of a whole run from ONE exact linear model --------------------------------
+// At >= ~8 samples per chip (config 5: 20 MS/s, 19.5 samples per chip) a run of S samples sees at most NB
+// chip boundaries, yet synth_fast_g pays two FP64 adds, a shift and a LOP3 per sample to find the chip.
+// Inside one binade [2^e, 2^(e+1)) the reference's chain is exactly linear, x_j = x_0 + j*delta with
+// delta = RN_ulp(x)(d) (see phase_chain: every sum is a multiple of ulp(x), hence exact - except in the one
+// binade where d is an exact half-ulp tie, which the caller excludes), so the sample at which chip c0+b
+// begins is n_b = min{ j : x_0 + j*delta >= c0 + b }: a quotient estimate from a job-wide 1/d (good to 1e-3
+// samples) corrected by two exact FMA tests.  The NB boundaries give a 32-bit sign mask for the run; a
+// sample then costs a select of +-gain (predicates straight from the mask: R2P), the carrier phase add, the
+// table address (shift + multiply-add), one LDS and one FFMA2 - 6.25 instead of 9 instructions, and the new
+// code phase is x_0 + S*delta, one more FMA.
+//
+// Preconditions (lin_ok(), voted per warp by the caller; otherwise synth_fast_g / synth_wrap run):
+//   * no 1023-chip wrap in the run (the caller's threshold test), c0 = floor(x_0) >= kLinMinChip,
+//   * no power of two in (c0, c0 + NB + 1]: x_0 .. x_0 + S*delta stays inside x_0's binade,
+//   * S * d < NB, and the row's tie binade is not one of [2^5, 2^10) (upload routes such rows to synth_wrap).
+constexpr int kLinMinChip = 32;
+GS_HD bool lin_ok(int c0, int nb)
+{
+    return c0 >= kLinMinChip && (uint32_t)(c0 ^ (c0 + nb + 1)) <= (uint32_t)c0;
+}
+GS_HD uint32_t shr_clamp(uint32_t v, uint32_t n) // v >> n, 0 for n >= 32
+{
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
+    return r;
+#else
+    return n >= 32u ? 0u : v >> n;
+#endif
+}
+template <class A, int S, int NB>
+GS_HD void synth_lin(typename A::acc_t (&acc)[S], double &x, uint32_t &phs, const double d, const uint32_t steps,
+                     const uint32_t gbits, const uint32_t win, const int c0, const double rinv0,
+                     const typename A::tab_t *lut, const uint32_t lane_off)
+{
+    const double c = dfrombits(dbits(x) & 0x7ff0000000000000ull); // 2^e: the binade of x
+    const double delta = dadd(dadd(c, d), -c);                    // RN_ulp(x)(d): what one step adds
+    double t = dadd(int_as_double_exact((uint32_t)c0 + 1u), -x);  // distance to the next chip, exact, in (0, 1]
+    uint32_t m = (uint32_t)((int32_t)win >> 31);                  // bit 31-j: sample j has chip sign "negative"
+    const uint32_t tw = win ^ (win << 1);                         // bit 31-b: chip c0+b+1 differs from chip c0+b
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        const double q = dfma_down(t, rinv0, 4503599627370496.0); // 2^52 + floor(t / d_nominal)
+        const double nf = dadd(q, -4503599627370496.0);
+        const double r0 = dfma(nf, delta, -t);                     // x_nf - (c0+b+1), exact
+        const double r1 = dadd(r0, delta);                         // x_(nf+1) - (c0+b+1), exact
+        // first sample at or past the boundary: the estimate is within one of it, on either side
+        const uint32_t n = (uint32_t)dbits(q) + (uint32_t)(dbits(r0) >> 63) + (uint32_t)(dbits(r1) >> 63);
+        const uint32_t flip = (uint32_t)((int32_t)(tw << b) >> 31);
+        m ^= flip & shr_clamp(0xffffffffu, n); // samples n.. change sign if the chips differ
+        t = dadd(t, 1.0);
+    }
+    // +-gain by a select on a bit of the mask (predicates straight from the mask's bytes, R2P + SEL on the ALU
+    // pipe).  The negated gain is made opaque: the compiler would otherwise rewrite the select as
+    // gbits ^ ((m << j) & 2^31), a shift on the FMA pipe - the busiest one of this loop - plus a LOP3.
+#ifdef __CUDA_ARCH__
+    uint32_t gneg;
+    asm("xor.b32 %0, %1, 0x80000000;" : "=r"(gneg) : "r"(gbits));
+#else
+    const uint32_t gneg = gbits ^ 0x80000000u;
+#endif
+#pragma unroll
+    for (int j = 0; j < S; j++) {
+        const uint32_t gs = (m & (0x80000000u >> j)) ? gneg : gbits;
+        A::mad_s(acc[j], lut_at<A>(lut, phs, lane_off), gs);
+        phs += steps;
+    }
+    x = dfma((double)S, delta, x);
+}
+
 // Per-thread, per-channel state of the integer-carrier kernel, 16 bytes in shared memory:
 //   x (f64) | carr_phase << 7, low 7 bits = icode0 + wraps so far in this epoch (<= 19 + 101) | fp32 bits of dataBit*gain
 GS_HD uint32_t lean_phase_word(uint32_t phs, int ic) { return (phs & ~127u) | (uint32_t)ic; }
@@ -708,7 +916,6 @@ GS_HD void synth_wrap(typename A::acc_t (&acc)[S], ChanState &st, const double d
 // power-of-two rescaling: every rounding commutes with it), so the index is floor(cph), again taken
 // with one round-down magic add (carrier_index).
 // =====================================================================================
-constexpr double kCarrMod = 512.0;
 
 GS_HD double carrier_step(double cph, const double dc) // gpssim.c:2245-2250, scaled by 512
 {

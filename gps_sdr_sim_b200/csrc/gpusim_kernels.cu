@@ -41,6 +41,20 @@ static cudaError_t set_attr_once(cudaFuncAttribute attr, int value)
 // ------------------------------------------------------------------------------------
 // K1
 // ------------------------------------------------------------------------------------
+// binade constants of one chain (phase_chain_tab) in shared memory: [field][binade][lane], conflict-free
+struct ChainTabSmem {
+    double *base; // this lane's column
+    __device__ __forceinline__ void set(int b, double delta, double lim, double r)
+    {
+        base[b * 32] = delta;
+        base[(kChainTabN + b) * 32] = lim;
+        base[(2 * kChainTabN + b) * 32] = r;
+    }
+    __device__ __forceinline__ double delta(int b) const { return base[b * 32]; }
+    __device__ __forceinline__ double lim(int b) const { return base[(kChainTabN + b) * 32]; }
+    __device__ __forceinline__ double r(int b) const { return base[(2 * kChainTabN + b) * 32]; }
+};
+
 template <bool kReplay>
 __global__ void __launch_bounds__(32) k1_chain(DeviceJob job)
 {
@@ -48,6 +62,7 @@ __global__ void __launch_bounds__(32) k1_chain(DeviceJob job)
     // from the pseudorange every epoch, but the signal is continuous, so the same satellite starts
     // consecutive epochs at almost the same code phase: the 32 chains of a warp cross binades and
     // wrap nearly in lockstep and the walk (a serial, latency-bound loop) hardly diverges.
+    __shared__ double tab_s[3 * kChainTabN * 32];
     if (blockIdx.x == 0 && threadIdx.x == 0)
         *job.work_counter = 0; // K2 of the same job runs after this kernel on the same stream
     const int groups = (job.n_epochs + 31) / 32;
@@ -56,46 +71,40 @@ __global__ void __launch_bounds__(32) k1_chain(DeviceJob job)
     const int k = blk % kMaxChan;
     const int e = (blk / kMaxChan) * 32 + threadIdx.x;
     const bool has_chain = e < job.n_epochs && k < job.nch[min(e, job.n_epochs - 1)];
-    const unsigned mask = __ballot_sync(0xffffffffu, has_chain);
     if (!has_chain)
         return;
+    ChainTabSmem tab;
+    tab.base = tab_s + threadIdx.x;
     const size_t row = (size_t)e * kMaxChan + k;
     if (carrier) {
         // the double carrier phase of a FLOAT_CARR_PHASE host (gpssim.c:2245-2250), scaled by 512
-        double *cc = job.ck_c + row * job.kc;
-        auto emit_c = [&](int j, double x, int) { cc[j] = x; };
+        double *cc = job.ck_c + ck_index(job.ck_e0 + e, k, 0, job.kc);
+        auto emit_c = [&](int j, double x, int) { cc[(size_t)j << 5] = x; };
         const int last = ((job.n_samples - 1) / job.chunk) * job.chunk;
         if (kReplay) {
             double x = job.cph0[row];
             for (int n = 0; n <= last; n++) {
                 if (n % job.chunk == 0)
-                    cc[n / job.chunk] = x;
+                    cc[(size_t)(n / job.chunk) << 5] = x;
                 x = carrier_step(x, job.dc[row]);
             }
         } else {
-            // rising and falling chains have their own walk (one wrap test, one jump direction); the lanes of
-            // a warp are the same satellite in consecutive epochs and almost always agree on the sign
-            const double dc = job.dc[row];
-            const unsigned falling = __ballot_sync(mask, dc < 0.0);
-            if (dc < 0.0)
-                phase_chain<-1>(job.cph0[row], dc, kCarrMod, last, job.chunk, emit_c, falling);
-            else
-                phase_chain<1>(job.cph0[row], dc, kCarrMod, last, job.chunk, emit_c, mask & ~falling);
+            carrier_chain(job.cph0[row], job.dc[row], last, job.chunk, tab, emit_c);
         }
         return;
     }
     const double d = job.rows[row].d;
     const double x0 = job.x0[row];
-    double *cx = job.ck_x + row * job.kc;
-    uint16_t *cw = job.ck_w + row * job.kc;
+    double *cx = job.ck_x + ck_index(job.ck_e0 + e, k, 0, job.kc);
+    uint16_t *cw = job.ck_w + ck_index(job.ck_e0 + e, k, 0, job.kc);
     auto emit = [&](int j, double x, int wraps) {
-        cx[j] = x;
-        cw[j] = (uint16_t)wraps;
+        cx[(size_t)j << 5] = x;
+        cw[(size_t)j << 5] = (uint16_t)wraps;
     };
     if (kReplay)
         code_chain_replay(x0, d, job.n_samples, job.chunk, emit);
     else
-        code_chain(x0, d, job.n_samples, job.chunk, emit, mask);
+        code_chain(x0, d, job.n_samples, job.chunk, tab, emit);
 }
 
 cudaError_t launch_chain(const DeviceJob &job, ChainAlgo algo, cudaStream_t stream)
@@ -408,7 +417,7 @@ __global__ void __maxnreg__(k2_max_regs(CF, SHARED_SM)) k2_synth(DeviceJob job)
             // chunk-start state of every channel
             uint32_t sa = sm.state;
             for (int k = 0; k < nc; k++, sa += G::kStride) {
-                const size_t ck = ((size_t)e * kMaxChan + k) * job.kc + jc;
+                const size_t ck = ck_index(job.ck_e0 + e, k, jc, job.kc);
                 const DevRow r = rows[k];
                 const int ic = (int)r.icode0 + (int)job.ck_w[ck];
                 const int bitk = ic / 20;
@@ -486,10 +495,10 @@ struct LeanSmem {
     uint32_t state;      // shared-window address of this thread's slot for channel 0
 };
 
-template <int FMT, int SR, bool UNI, bool PF>
+template <int FMT, int SR, bool UNI, bool PF, int NB>
 __device__ __forceinline__ void lean_run(const LeanSmem &sm, const uint4 *rows4, const int nc, const int ncw,
                                          const bool live, const unsigned mask, const uint32_t lane_off,
-                                         const uint32_t cthr_mask, uint8_t *dst)
+                                         const uint32_t cthr_mask, const DeviceJob &job, uint8_t *dst)
 {
     typedef AccF32x2 A;
     A::acc_t acc[SR];
@@ -527,8 +536,14 @@ __device__ __forceinline__ void lean_run(const LeanSmem &sm, const uint4 *rows4,
             const uint2 ww = lds_u32x2(sm.win_s + (r0.w >> 16) + (((uint32_t)c0 >> 5) << 3)); // {word i+1, word i}
             const uint32_t win = funnel_l_wrap(ww.x, ww.y, (uint32_t)c0);
             uint32_t phs = st.z;
+            // low chip rate (NB > 0): when every lane's run stays inside one binade, the chips of the run come
+            // from the exact linear model (synth_lin) instead of two FP64 adds and a shift per sample
+            const bool all_lin = NB > 0 && !any_wrap && __all_sync(UNI ? 0xffffffffu : __activemask(), lin_ok(c0, NB));
             if (!any_wrap) {
-                synth_fast_g<A, SR>(acc, x, phs, d, r0.z, st.w, win, magic, sm.lut, lane_off);
+                if (all_lin)
+                    synth_lin<A, SR, (NB > 0 ? NB : 1)>(acc, x, phs, d, r0.z, st.w, win, c0, job.lin_rinv, sm.lut, lane_off);
+                else
+                    synth_fast_g<A, SR>(acc, x, phs, d, r0.z, st.w, win, magic, sm.lut, lane_off);
                 sts_f64(sa, x);
                 sts_u32(sa + 8u, phs);
             } else {
@@ -550,7 +565,7 @@ __device__ __forceinline__ void lean_run(const LeanSmem &sm, const uint4 *rows4,
         store_run<A, FMT, SR>(dst, acc);
 }
 
-template <int FMT, int S, bool SHARED_SM>
+template <int FMT, int S, bool SHARED_SM, int NB>
 __global__ void __maxnreg__(k2_max_regs(0, SHARED_SM)) k2_lean(DeviceJob job)
 {
     typedef AccF32x2 A;
@@ -619,7 +634,7 @@ __global__ void __maxnreg__(k2_max_regs(0, SHARED_SM)) k2_lean(DeviceJob job)
             // chunk-start state of every channel
             uint32_t sa = sm.state;
             for (int k = 0; k < nc; k++, sa += kLeanStride) {
-                const size_t ck = ((size_t)e * kMaxChan + k) * job.kc + jc;
+                const size_t ck = ck_index(job.ck_e0 + e, k, jc, job.kc);
                 const DevRow r = rows[k];
                 const int ic = (int)r.icode0 + (int)job.ck_w[ck];
                 const double x = job.ck_x[ck];
@@ -639,31 +654,31 @@ __global__ void __maxnreg__(k2_max_regs(0, SHARED_SM)) k2_lean(DeviceJob job)
 
             if (uni) {
                 for (int i = 0; i < full_w; i++)
-                    lean_run<FMT, S, true, PF>(sm, rows4, nc, ncw, true, mask, lane_off, cthr_mask,
+                    lean_run<FMT, S, true, PF, NB>(sm, rows4, nc, ncw, true, mask, lane_off, cthr_mask, job,
                                            outp + (size_t)i * (S / 8) * kBytesPer8);
             } else {
                 for (int i = 0; i < full_w; i++)
-                    lean_run<FMT, S, false, PF>(sm, rows4, nc, ncw, i < full, mask, lane_off, cthr_mask,
+                    lean_run<FMT, S, false, PF, NB>(sm, rows4, nc, ncw, i < full, mask, lane_off, cthr_mask, job,
                                             outp + (size_t)i * (S / 8) * kBytesPer8);
             }
             for (int i = 0; i < tail_w; i++)
-                lean_run<FMT, 8, false, PF>(sm, rows4, nc, ncw, i < tail8, mask, lane_off, cthr_mask,
+                lean_run<FMT, 8, false, PF, NB>(sm, rows4, nc, ncw, i < tail8, mask, lane_off, cthr_mask, job,
                                         outp + ((size_t)full * (S / 8) + i) * kBytesPer8);
         }
         __syncwarp();
     }
 }
 
-template <int FMT, int S, bool SHARED_SM = false>
+template <int FMT, int S, bool SHARED_SM = false, int NB = 0>
 static cudaError_t launch_lean(const DeviceJob &job, cudaStream_t stream)
 {
     const size_t smem = lean_smem_bytes(job.max_active);
-    cudaError_t err = set_attr_once<k2_lean<FMT, S, SHARED_SM>>(cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lean_smem_bytes(kMaxChan));
+    cudaError_t err = set_attr_once<k2_lean<FMT, S, SHARED_SM, NB>>(cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lean_smem_bytes(kMaxChan));
     if (err != cudaSuccess)
         return err;
     const long long warps_per_block = kK2Threads / 32;
     const int blocks = (int)std::min<long long>(std::max(1, job.sm_count), ((long long)job.n_units + warps_per_block - 1) / warps_per_block);
-    k2_lean<FMT, S, SHARED_SM><<<blocks, kK2Threads, smem, stream>>>(job);
+    k2_lean<FMT, S, SHARED_SM, NB><<<blocks, kK2Threads, smem, stream>>>(job);
     return cudaGetLastError();
 }
 
@@ -686,7 +701,7 @@ __global__ void __launch_bounds__(128) k2_generic(DeviceJob job)
 
     GenericChan ch[kMaxChan];
     for (int k = 0; k < nc; k++) {
-        const size_t ck = ((size_t)e * kMaxChan + k) * job.kc + jc;
+        const size_t ck = ck_index(job.ck_e0 + e, k, jc, job.kc);
         const DevRow r = rows[k];
         const int ic = (int)r.icode0 + (int)job.ck_w[ck];
         ch[k].x = job.ck_x[ck];
@@ -752,6 +767,10 @@ static cudaError_t launch_tuned(const DeviceJob &job, cudaStream_t stream)
         return launch_tuned_a<AccF32x2, FMT, 16, 1>(job, stream);
     }
     if (job.accum == 1 && job.lean) {
+        if (S == 32 && job.lin_nb == 2)
+            return launch_lean<FMT, 32, false, 2>(job, stream);
+        if (S == 32 && job.lin_nb == 4)
+            return launch_lean<FMT, 32, false, 4>(job, stream);
         if (S == 32 && job.shared_sm)
             return launch_lean<FMT, 32, true>(job, stream);
         return launch_lean<FMT, S>(job, stream);

@@ -15,11 +15,11 @@ struct DeviceJob {
     const DevRow *rows;      // [n_epochs][16], active channels compacted to the front
     const uint8_t *nch;      // [n_epochs] active channel count
     const double *x0;        // [n_epochs][16] code_phase at epoch start
-    double *ck_x;            // [n_epochs][16][kc] code phase at sample j*chunk
-    uint16_t *ck_w;          // [n_epochs][16][kc] 1023-chip wraps before sample j*chunk
+    double *ck_x;            // code phase at sample j*chunk, at ck_index(ck_e0 + e, channel, j, kc)
+    uint16_t *ck_w;          // 1023-chip wraps before sample j*chunk, same index
     const double *dc;        // FLOAT hosts: [n_epochs][16] 512*RN(f_carr*delt)
     const double *cph0;      // FLOAT hosts: [n_epochs][16] 512*carr_phase at epoch start
-    double *ck_c;            // FLOAT hosts: [n_epochs][16][kc] 512*carr_phase at sample j*chunk
+    double *ck_c;            // FLOAT hosts: 512*carr_phase at sample j*chunk, same index
     const int32_t *lut_wide; // [512] AccWide::table_entry(cos, sin)
     const uint64_t *lut_f32; // [512] AccF32x2::table_entry(cos, sin)
     const int16_t *sin16;    // [512] plain tables for the generic kernel
@@ -28,6 +28,7 @@ struct DeviceJob {
     uint8_t *out;            // n_epochs * epoch_bytes
     unsigned int *work_counter; // zeroed by K1, handed out by K2's warps (32 chunks per unit)
     int32_t n_epochs;
+    int32_t ck_e0;           // epoch of rows[0] inside the checkpoint arrays (a sub-range of the job K1 ran for)
     int32_t n_samples;       // samples per epoch
     int32_t chunk;           // samples per thread chunk (multiple of 8; of 32 when ppe == 0)
     int32_t kc;              // chunks per epoch = ceil(n_samples/chunk)
@@ -43,8 +44,19 @@ struct DeviceJob {
     int32_t carrier_float;   // 1: FLOAT_CARR_PHASE host (double carrier phase), 0: integer carrier
     int32_t shared_sm;       // 1: K2 build that leaves registers for the next call's K1 (see k2_max_regs)
     int32_t lean;            // 1: integer carrier runs k2_lean (default), 0: the round-1 k2_synth (kept as a cross-check)
+    int32_t lin_nb;          // > 0: low chip rate - runs that qualify take synth_lin with this many chip boundaries (2 or 4)
+    double lin_rinv;         // synth_lin: job-wide estimate of 1 / (f_code*delt)
     int32_t float_narrow;    // 1: FLOAT hosts always use the 384-thread build (test hook, see K2Geom)
 };
+
+// Checkpoints are stored in blocks of 32 consecutive epochs, epoch fastest: the chain kernel's warps are one
+// channel over 32 consecutive epochs, so the 32 lanes' values of checkpoint j are one 256-byte run (a scattered
+// store costs the LSU one cycle per 32-byte sector: 0.26 of the chain kernel's 0.44 ms went there, ncu r02).
+__host__ __device__ inline size_t ck_index(int e, int k, int j, int kc)
+{
+    return ((((size_t)(e >> 5) * kMaxChan + (size_t)k) * (size_t)kc + (size_t)j) << 5) + (size_t)(e & 31);
+}
+__host__ __device__ inline size_t ck_elems(int n_epochs, int kc) { return (size_t)((n_epochs + 31) / 32) * 32 * kMaxChan * (size_t)kc; }
 
 enum class ChainAlgo { Jump = 0, Replay = 1 };
 enum class SynthKernel { Tuned32 = 0, Tuned16 = 1, Generic = 2 };

@@ -139,8 +139,8 @@ double gpusim_advance_carrier_f64(double carr_phase, double f_carr, double delt,
         return carr_phase;
     auto nothing = [](int, double, int) {};
     const double x0 = carr_phase * 512.0, d512 = (double)d * 512.0;
-    return (d512 < 0.0 ? gpusim::phase_chain<-1>(x0, d512, 512.0, n_samples, 1 << 30, nothing)
-                       : gpusim::phase_chain<1>(x0, d512, 512.0, n_samples, 1 << 30, nothing)) / 512.0;
+    gpusim::ChainTabHost tab;
+    return gpusim::carrier_chain(x0, d512, n_samples, 1 << 30, tab, nothing) / 512.0;
 }
 
 } // extern "C"

@@ -99,6 +99,12 @@ struct LeanSlot {
     double x;
     uint32_t phase_word, gain_bits;
 };
+// low chip rate: chip boundaries per run the linear model (synth_lin) is instantiated for (0 = off) and the job-wide
+// estimate of 1 / (f_code*delt); set per table by emu_generate exactly as gpusim_upload_table / plan_job do
+static int g_lin_nb = 0;
+static double g_lin_rinv = 0.0;
+static long g_lin_runs = 0, g_fast_runs = 0; // (run, channel) pairs that took synth_lin / synth_fast_g since the last emu_generate
+
 template <int FMT, int SR>
 void emu_run_lean(const Tables &T, const std::vector<uint32_t> &win64, const DevRow *rows, int nc, LeanSlot *st,
                   int force_wrap, uint32_t lane_off, uint8_t *dst)
@@ -118,7 +124,14 @@ void emu_run_lean(const Tables &T, const std::vector<uint32_t> &win64, const Dev
         const uint32_t win = funnel_l_wrap(ww[0], ww[1], (uint32_t)c0);
         uint32_t phs = st[k].phase_word;
         if (!wrap) {
-            synth_fast_g<A, SR>(acc, x, phs, r.d, (uint32_t)r.steps, st[k].gain_bits, win, magic, lut, lane_off);
+            // the device votes per warp; every path computes the same samples, so one lane may decide for itself
+            ((g_lin_nb > 0 && lin_ok(c0, g_lin_nb)) ? g_lin_runs : g_fast_runs)++;
+            if (g_lin_nb == 2 && lin_ok(c0, 2))
+                synth_lin<A, SR, 2>(acc, x, phs, r.d, (uint32_t)r.steps, st[k].gain_bits, win, c0, g_lin_rinv, lut, lane_off);
+            else if (g_lin_nb == 4 && lin_ok(c0, 4))
+                synth_lin<A, SR, 4>(acc, x, phs, r.d, (uint32_t)r.steps, st[k].gain_bits, win, c0, g_lin_rinv, lut, lane_off);
+            else
+                synth_fast_g<A, SR>(acc, x, phs, r.d, (uint32_t)r.steps, st[k].gain_bits, win, magic, lut, lane_off);
             st[k].x = x;
             st[k].phase_word = phs;
         } else {
@@ -283,6 +296,23 @@ int emu_generate(const gpusim_epoch_table *t, int N, double delt, int fmt, int c
                  int force_wrap, int chain_replay, int accum, int carrier_float, uint8_t *out)
 {
     static const Tables T;
+    // low chip rate: the rule of gpusim_upload_table / plan_job (accum == 1 is the lean kernel; accum == 5 is
+    // the lean kernel with the linear path switched off, option lowrate=0)
+    g_lin_nb = 0;
+    g_lin_runs = g_fast_runs = 0;
+    double dmin = 1e300, dmax = 0.0;
+    for (size_t r = 0; r < (size_t)t->n_epochs * kMaxChan; r++)
+        if (t->prn[r] > 0) {
+            const double d = dmul(t->f_code[r], delt);
+            dmin = std::min(dmin, d);
+            dmax = std::max(dmax, d);
+        }
+    if (!carrier_float && accum == 1 && kernel == 0 && dmax > 0.0 && 32.0 * dmax < 4.0 && 5.0 * (dmax - dmin) < 0.25 * dmin * dmin) {
+        g_lin_nb = 32.0 * dmax < 2.0 ? 2 : 4;
+        g_lin_rinv = 2.0 / (dmin + dmax);
+    }
+    if (accum == 5)
+        accum = 1;
     const size_t eb = fmt == 1 ? (size_t)(N / 4) : fmt == 8 ? (size_t)2 * N : (size_t)4 * N;
     const int kc = (N + chunk - 1) / chunk;
     // tuned kernels: chunks and epochs of a multiple of 8 samples (runs of 32/16 plus 8-sample tails)
@@ -304,6 +334,8 @@ int emu_generate(const gpusim_epoch_table *t, int N, double delt, int fmt, int c
             o.d = dmul(t->f_code[r], delt);
             o.steps = carrier_float ? 0 : (int32_t)((uint32_t)t->carr_phasestep[r] << 7);
             o.cthr_prn = pack_cthr_prn(o.d, t->prn[r]);
+            if (g_lin_nb > 0 && chain_tie_binade(o.d) >= 5 && chain_tie_binade(o.d) <= 9)
+                o.cthr_prn &= (uint16_t)~kCthrMask; // exact tie in a binade of the linear model: always the per-sample loop
             o.woff = (uint16_t)(t->prn[r] * kCaWinBytes);
             o.gain = t->gain[r];
             o.ph0s = carrier_float ? 0u : t->carr_phase[r] << 7;
@@ -341,7 +373,7 @@ int emu_generate(const gpusim_epoch_table *t, int N, double delt, int fmt, int c
                         x = carrier_step(x, dcs[k]);
                     }
                 } else {
-                    phase_chain(cph0[k], dcs[k], kCarrMod, last, chunk, emit_c);
+                    { ChainTabHost tab; carrier_chain(cph0[k], dcs[k], last, chunk, tab, emit_c); }
                 }
             }
         }
@@ -373,6 +405,37 @@ int emu_generate(const gpusim_epoch_table *t, int N, double delt, int fmt, int c
     }
     return 0;
 }
+
+// One run of 32 samples of one channel through synth_lin<NB> and through synth_fast_g from the same state:
+// returns 1 when the accumulators, the code phase and the carrier phase after the run agree bit for bit.
+// x_end[0] / x_end[1]: the code phase after the run (linear model / per-sample chain).
+int emu_lin_matches_fast(double x0, double d, uint32_t phs0, int32_t steps, int prn, int nb, double rinv, double *x_end)
+{
+    static const Tables T;
+    typedef AccF32x2 A;
+    const A::tab_t *lut = table_of<A>(T);
+    int c0;
+    const double magic = floor_magic(x0, c0);
+    const uint32_t win = chip_window(T.negw.data() + (size_t)prn * kCaWords, c0);
+    const uint32_t gb = A::gain_bits(77);
+    A::acc_t a[32], b[32];
+    for (int j = 0; j < 32; j++)
+        a[j] = b[j] = A::init();
+    double xa = x0, xb = x0;
+    uint32_t pa = phs0, pb = phs0;
+    if (nb == 2)
+        synth_lin<A, 32, 2>(a, xa, pa, d, (uint32_t)steps, gb, win, c0, rinv, lut, 8u);
+    else
+        synth_lin<A, 32, 4>(a, xa, pa, d, (uint32_t)steps, gb, win, c0, rinv, lut, 8u);
+    synth_fast_g<A, 32>(b, xb, pb, d, (uint32_t)steps, gb, win, magic, lut, 8u);
+    x_end[0] = xa;
+    x_end[1] = xb;
+    return memcmp(a, b, sizeof(a)) == 0 && dbits(xa) == dbits(xb) && pa == pb;
+}
+
+// how many (run, channel) pairs of the last emu_generate call took the linear low-chip-rate path / the per-sample loop
+long emu_lin_runs(void) { return g_lin_runs; }
+long emu_fast_runs(void) { return g_fast_runs; }
 
 // the chain walk alone: checkpoints every `every` samples
 void emu_code_chain(double x0, double d, int n_total, int every, int replay, double *x_out, int *w_out)
@@ -407,6 +470,17 @@ double emu_phase_chain_signed(double x0, double d, double M, int n_end, int ever
         w_out[j] = wraps;
     };
     return d < 0.0 ? phase_chain<-1>(x0, d, M, n_end, every, emit) : phase_chain<1>(x0, d, M, n_end, every, emit);
+}
+
+// the tabulated walk (phase_chain_tab): what k1_chain runs on the device and gpusim_advance_carrier_f64 on the host; M <= 1024
+double emu_phase_chain_tab(double x0, double d, double M, int n_end, int every, double *x_out, int *w_out)
+{
+    auto emit = [&](int j, double x, int wraps) {
+        x_out[j] = x;
+        w_out[j] = wraps;
+    };
+    ChainTabHost tab;
+    return d < 0.0 ? phase_chain_tab<-1>(x0, d, M, n_end, every, tab, emit) : phase_chain_tab<1>(x0, d, M, n_end, every, tab, emit);
 }
 
 } // extern "C"

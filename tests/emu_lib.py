@@ -45,13 +45,18 @@ def lib() -> ctypes.CDLL:
                                          ctypes.c_void_p, ctypes.c_void_p]
         _lib.emu_phase_chain_signed.restype = ctypes.c_double
         _lib.emu_phase_chain_signed.argtypes = _lib.emu_phase_chain.argtypes
+        _lib.emu_lin_runs.restype = ctypes.c_long
+        _lib.emu_fast_runs.restype = ctypes.c_long
+        _lib.emu_phase_chain_tab.restype = ctypes.c_double
+        _lib.emu_phase_chain_tab.argtypes = _lib.emu_phase_chain.argtypes
     return _lib
 
 
 def generate(table, chunk: int = 512, kernel: int = TUNED32, force_wrap: bool = False,
              chain_replay: bool = False, accum: int = 1) -> np.ndarray:
     """accum: 1 = what the product launches (k2_lean for integer carrier, k2_synth<AccF32x2> for double carrier),
-    3 = k2_synth<AccF32x2> for integer carrier (option lean=0), 0 = k2_synth<AccWide> (option accum=0)."""
+    3 = k2_synth<AccF32x2> for integer carrier (option lean=0), 0 = k2_synth<AccWide> (option accum=0),
+    5 = the lean kernel without the linear low-chip-rate path (option lowrate=0)."""
     out = np.zeros(table.n_epochs * table.epoch_bytes, dtype=np.uint8)
     c = table.as_c()
     rc = lib().emu_generate(ctypes.addressof(c), table.samples_per_epoch, table.delt, table.data_format, chunk,
@@ -59,6 +64,20 @@ def generate(table, chunk: int = 512, kernel: int = TUNED32, force_wrap: bool = 
     if rc != 0:
         raise ValueError("table outside the selected kernel's ranges")
     return out
+
+
+def lin_matches_fast(x0: float, d: float, phs0: int, steps: int, prn: int, nb: int, rinv: float):
+    """One run of 32 samples of one channel through synth_lin<nb> and synth_fast_g from the same state:
+    (everything agrees bit for bit, code phase after the run [linear model, per-sample chain])."""
+    xe = (ctypes.c_double * 2)()
+    ok = lib().emu_lin_matches_fast(ctypes.c_double(x0), ctypes.c_double(d), ctypes.c_uint32(phs0), ctypes.c_int32(steps),
+                                    prn, nb, ctypes.c_double(rinv), xe)
+    return bool(ok), (xe[0], xe[1])
+
+
+def path_counts():
+    """(run, channel) pairs of the last generate() that took (synth_lin, synth_fast_g)."""
+    return int(lib().emu_lin_runs()), int(lib().emu_fast_runs())
 
 
 def code_chain(x0: float, d: float, n: int, every: int, replay: bool = False):
@@ -80,4 +99,10 @@ def phase_chain(x0: float, d: float, modulus: float, n_end: int, every: int):
     end_s = lib().emu_phase_chain_signed(x0, d, modulus, n_end, every, xs.ctypes.data, ws.ctypes.data)
     assert np.array_equal(x.view(np.uint64), xs.view(np.uint64)) and np.array_equal(w, ws)
     assert np.float64(end).view(np.uint64) == np.float64(end_s).view(np.uint64)
+    # and so must the tabulated walk (phase_chain_tab: k1_chain on the device, gpusim_advance_carrier_f64 on the host)
+    if modulus <= 1024.0:
+        xt, wt = np.empty_like(x), np.empty_like(w)
+        end_t = lib().emu_phase_chain_tab(x0, d, modulus, n_end, every, xt.ctypes.data, wt.ctypes.data)
+        assert np.array_equal(x.view(np.uint64), xt.view(np.uint64)) and np.array_equal(w, wt)
+        assert np.float64(end).view(np.uint64) == np.float64(end_t).view(np.uint64)
     return x, w, end

@@ -277,3 +277,22 @@ def test_kernels_stay_inside_their_buffers(gpu_required, monkeypatch):
             assert digests(got, table) == want
             assert int((whole[:G] != 0xA5).sum()) == 0 and int((whole[G + table.n_epochs * eb:] != 0xA5).sum()) == 0, name
             assert sim.guard_violations() == 0, name
+
+
+@pytest.mark.parametrize("n,fmt,nch,opts", [
+    (2000000, gs.SC16, 11, {}),                       # config 5 shape: 20 MS/s, linear path with 2 boundaries per run
+    (2000000, gs.SC08, 13, {"layout": 1, "chunk": 512}),
+    (1600000, gs.SC01, 16, {}),
+    (1000000, gs.SC16, 12, {}),                       # 10 MS/s: the 4-boundary build
+    (840000, gs.SC08, 9, {"layout": 1, "chunk": 1024}),
+    (2000000, gs.SC16, 11, {"lowrate": 0}),           # the per-sample loop on the same rows
+])
+def test_low_chip_rate_linear_path(n, fmt, nch, opts):
+    """>= 8 samples per chip: chips of a run from the exact linear model (synth_lin) - bytes of the oracle."""
+    t = gs.synthetic_table(3, n, nch, fmt, seed=n // 1000 + fmt)
+    with gs.GpuSim.for_table(t) as sim:
+        for k, v in opts.items():
+            sim.set_option(k, v)
+        out = sim.generate_epochs(t)
+        assert sim.timing().fast_path == 1
+    assert np.array_equal(out, oracle_lib.generate(t))

@@ -388,7 +388,9 @@ def main_b200(args):
     overlapped = bool(t.chain_overlapped) if hasattr(t, "chain_overlapped") else None
     # average duration of the synthesis kernel's launches over the timed region: the launch stream carries the
     # K2 launches back to back (and the chain kernels too unless the library runs them on its own stream)
-    k2 = ms / args.steps - (0.0 if overlapped else k1_last_ms)
+    # (option pipeline >= 1 puts the chain kernel on the library's own stream; it then overlaps the tail of the
+    # previous synthesis kernel at most, so the last step's own K2 events are the better figure there)
+    k2 = k2_last_ms if overlapped else ms / args.steps - k1_last_ms
     launches_per_step = t.launches
     fast_path = t.fast_path
 

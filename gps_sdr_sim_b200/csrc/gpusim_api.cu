@@ -24,7 +24,6 @@ namespace {
 thread_local std::string g_create_error;
 
 constexpr size_t kStageBytes = 64u << 20;      // one pinned staging buffer / sub-batch of output
-constexpr int kOverlapMinSamples = 208000; // samples per epoch from which K1 is overlapped with the previous K2
 constexpr size_t kCheckpointBudget = 1u << 29; // device bytes for ONE set of K1 checkpoints (there are two)
 
 } // namespace
@@ -74,7 +73,7 @@ struct gpusim_ctx {
     uint8_t *h_stage[2] = {nullptr, nullptr};
 
     // options
-    int opt_chunk = 0, opt_force_generic = 0, opt_force_slow = 0, opt_chain_replay = 0, opt_accum = 1, opt_layout = 0, opt_pipeline = 1, opt_float_geom = 0, opt_lean = 1, opt_lowrate = 1;
+    int opt_chunk = 0, opt_force_generic = 0, opt_force_slow = 0, opt_chain_replay = 0, opt_accum = 1, opt_layout = 0, opt_pipeline = 0, opt_float_geom = 0, opt_lean = 1, opt_lowrate = 1;
     int opt_direct_first_mb = 16, opt_direct_mb = 64; // sub-batch sizes when copying straight into the caller's buffer
 
     gpusim_timing timing{};
@@ -187,7 +186,6 @@ SynthKernel plan_job(gpusim_ctx *ctx, int first, int n, uint8_t *out_dev, Device
     job.negw = ctx->d_negw;
     job.out = out_dev;
     job.work_counter = ctx->d_work + 8 * slot;
-    job.shared_sm = 0;
     job.sm_count = ctx->sm_count;
     job.n_epochs = n;
     job.n_samples = ctx->cfg.samples_per_epoch;
@@ -265,10 +263,13 @@ DeviceJob sub_job(const gpusim_ctx *ctx, const DeviceJob &whole, int first, int 
     return job;
 }
 
-// Launch K1 + K2 for uploaded epochs [first, first+n) into out_dev.  K2 runs on `stream`; K1 runs on
-// the library's chain stream as soon as the checkpoint slot is free, i.e. concurrently with the K2 of
-// the PREVIOUS call when calls are issued back to back (a stream of batches).  K1 is a latency-bound
-// kernel of a few warps per SM; K2 is built to leave it the registers it needs.
+// Launch K1 + K2 for uploaded epochs [first, first+n) into out_dev.  K2 runs on `stream`.  When calls are
+// issued back to back (a stream of batches) and the previous call's K2 is still in flight, K1 of this call
+// goes to the library's chain stream instead: it then starts on the SMs the previous K2 has already left (a
+// persistent kernel drains over its last work unit) instead of waiting for its last block.  The two sets of
+// checkpoints and work counters the calls alternate between make that safe.  Option pipeline: 0 never
+// (default: with the chain kernel at 0.2 ms the two orders time the same, 4.27 against 4.28 ms per step),
+// 1 when the previous K2 is still running, 2 always.
 int launch_range(gpusim_ctx *ctx, int first, int n, uint8_t *out_dev, cudaStream_t stream)
 {
     if (n <= 0)
@@ -276,18 +277,11 @@ int launch_range(gpusim_ctx *ctx, int first, int n, uint8_t *out_dev, cudaStream
     const int slot = (int)(ctx->seq++ & 1u);
     DeviceJob job;
     const SynthKernel which = plan_job(ctx, first, n, out_dev, job, slot);
-    // Overlap pays when the synthesis kernel outlasts a chain kernel that is squeezed into the
-    // registers K2 leaves free (there it runs ~4x slower than alone, and both scale with epochs x
-    // channels, so the criterion is the epoch length): measured break-even near 200 000 samples per
-    // epoch.  FLOAT and the rarely used kernels have no shared-SM build (synth_has_shared_sm_build) - same
-    // stream for them.
-    // And only when there is something to overlap with: the previous call's K2 is still in flight.
-    bool overlap = ctx->opt_pipeline != 0 && synth_has_shared_sm_build(job, which);
+    bool overlap = ctx->opt_pipeline != 0;
     if (overlap && ctx->opt_pipeline != 2) {
-        overlap = job.n_samples >= kOverlapMinSamples && cudaEventQuery(ctx->ev_s1[slot ^ 1]) == cudaErrorNotReady;
+        overlap = cudaEventQuery(ctx->ev_s1[slot ^ 1]) == cudaErrorNotReady;
         (void)cudaGetLastError(); // "not ready" is an answer, not an error
     }
-    job.shared_sm = overlap ? 1 : 0;
     cudaStream_t cs = overlap ? ctx->s_chain : stream;
     GS_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_s1[slot], 0)); // K2 of two calls ago read this slot
     GS_CUDA(ctx, cudaEventRecord(ctx->ev_c0[slot], cs));

@@ -539,7 +539,9 @@ GS_HD double phase_chain(double x, const double d, const double M, const int n_e
 // ---- the same walk with the binade constants tabulated up front ------------------------------------
 // phase_chain() derives the constants of a binade whenever the chain enters it - on a GPU that is most of
 // the instructions of a trip (ncu, round 2: ~130 SASS instructions per trip, 6 cycles each on a lone
-// in-order warp).  The constants depend on d only, and a chain below M <= 1024 only ever visits the binades
+// in-order warp).  (On the host's out-of-order cores phase_chain() stays the faster walk - the constants of
+// the next binade are computed in the shadow of the current jump, where this one has a table lookup on its
+// serial path: 31 against 44 us per epoch of a 1.5 kHz carrier - so gpusim_advance_carrier_f64 keeps it.)  The constants depend on d only, and a chain below M <= 1024 only ever visits the binades
 // [2^-4, 2^10): phase_chain_tab() tabulates them once per chain (14 entries x {delta, lim, r}, shared
 // memory on the device, the stack on the host) and a trip is then: three loads, lim - x, one round-down
 // fused multiply-add (the floor of the jump count), the jump itself (one FMA) and the real step - the
@@ -559,19 +561,15 @@ struct ChainTabHost {                 // host / emulation storage; the device us
     GS_HD double lim(int b) const { return v[1][b]; }
     GS_HD double r(int b) const { return v[2][b]; }
 };
-GS_HD double dfma_down(double a, double b, double c) // the exact a*b + c rounded towards -infinity
+GS_HD double dfma_down(double a, double b, double c) // 2^52 + floor(a * b), for c = 2^52 and 0 <= |a * b| < 2^31
 {
 #ifdef __CUDA_ARCH__
-    return __fma_rd(a, b, c);
+    return __fma_rd(a, b, c); // the exact product, one rounding (towards -infinity)
 #else
-    // host: only called with c = 2^52 and |a*b| < 2^31: the rounded-down sum is 2^52 + floor(a*b); a*b is
-    // evaluated exactly as a double-double (fma gives the rounding error of the product)
-    const double p = a * b;
-    const double e = __builtin_fma(a, b, -p); // a*b = p + e exactly
-    double f = __builtin_floor(p);
-    if (f == p && e < 0.0)
-        f -= 1.0; // the exact product lies just below the integer p
-    return c + f;
+    // host: the product rounded to nearest first.  Both are lower bounds of the number of steps that fit (the
+    // margin in r covers a rounding of the product, see phase_chain), and any count up to the bound gives the
+    // same chain - the host and the device may split a binade into different jumps, never into different values.
+    return c + __builtin_floor(a * b);
 #endif
 }
 
@@ -605,18 +603,24 @@ GS_HD double phase_chain_tab(double x, const double d, const double M, const int
     // emits checkpoint j at the same point of the program - one coalesced store per warp - whatever the number
     // of trips each lane needed to get there, and no trip is spent on stopping at a checkpoint.
     int n = 0, wraps = 0, k = 0;
-    double delta = 0.0;
+    double delta = 0.0, kf = 0.0;
     auto open_segment = [&]() {
         const uint64_t xb = dbits(x);
         int bi = (int)(xb >> 52) - kChainTabLo; // x in [0, M), M <= 1024: bi <= 13
         bi = bi < 0 ? 0 : bi;
-        const double room = neg ? dadd(x, -tab.lim(bi)) : dadd(tab.lim(bi), -x);
-        const double m1 = dfma_down(room, tab.r(bi), 4503599627370496.0); // 2^52 + floor(room * r)
+        // no jump (k = 0) is "r = 0" or "room = 0" BEFORE the multiply, so that k and (double)k both come straight
+        // out of the one round-down multiply-add: the untabulated binades have r = 0 in the table; an exact tie
+        // from an odd significand takes its real step first; a falling chain sitting on the binade's lower edge
+        // has room = -ulp
+        double r = tab.r(bi);
+        if (bi == tie_bi && (xb & 1u))
+            r = 0.0;
+        double room = neg ? dadd(x, -tab.lim(bi)) : dadd(tab.lim(bi), -x);
+        if (neg && room < 0.0)
+            room = 0.0;
+        const double m1 = dfma_down(room, r, 4503599627370496.0); // 2^52 + floor(room * r)
         k = (int)(uint32_t)dbits(m1);
-        // no jump: an exact tie from an odd significand takes its real step first; a falling chain sitting on
-        // the binade's lower edge has room < 0; the untabulated binades have r = 0
-        if ((bi == tie_bi && (xb & 1u)) || (neg && k < 0))
-            k = 0;
+        kf = dadd(m1, -4503599627370496.0);
         delta = tab.delta(bi);
     };
     auto value_at = [&](int target) { // target - n in [0, k]
@@ -626,7 +630,7 @@ GS_HD double phase_chain_tab(double x, const double d, const double M, const int
     int j = 0;
     for (int target = 0;;) {
         while (target - n > k) {
-            x = dfma(int_as_double_exact((uint32_t)k), delta, x);
+            x = dfma(kf, delta, x);
             x = dadd(x, d);
             if (!neg) {
                 if (x >= M) {

@@ -183,15 +183,13 @@ template <int CF> struct K2Geom {
     static constexpr uint32_t kMeta = CF ? 16u * kThreads : 8u * kThreads + 4u;
 };
 
-// Register cap of the synthesis kernel.  Normally one block owns the SM (launch bound: 128 registers
-// at 512 threads, 168 at 384).  The "shared SM" builds of the 512-thread kernels are capped at 112:
-// that leaves 2048 of the 16384 registers of every SM sub-partition free (4 warps x 32 lanes x 112 =
-// 14336), room for two warps of the NEXT call's chain kernel (k1_chain: 32-thread blocks, 32
-// registers) beside the resident block.  At 120 nothing fits (measured: no overlap); at 112 the
-// chain kernel disappears behind the synthesis kernel, which itself gets ~4 % slower.
-constexpr int k2_max_regs(int cf, bool shared_sm)
+// Register cap of the synthesis kernel: one block owns the SM (128 registers at 512 threads, 168 at 384).
+// (Round 1 also shipped 112-register builds of the 512-thread kernels that left room for the next call's chain
+// kernel on the same SM; with the chain kernel at 0.2 ms instead of 0.53 ms they no longer pay - a 4 % slower
+// synthesis kernel to hide 5 % - and are gone.)
+constexpr int k2_max_regs(int cf)
 {
-    return shared_sm ? 112 : (cf == 1 ? ((65536 / kK2ThreadsFloat) > 255 ? 255 : (65536 / kK2ThreadsFloat) / 8 * 8) : 128);
+    return cf == 1 ? ((65536 / kK2ThreadsFloat) > 255 ? 255 : (65536 / kK2ThreadsFloat) / 8 * 8) : 128;
 }
 
 size_t synth_smem_bytes_float(int max_active)
@@ -337,8 +335,8 @@ __device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows
         store_run<A, FMT, SR>(dst, acc);
 }
 
-template <class A, int FMT, int S, int CF, bool SHARED_SM>
-__global__ void __maxnreg__(k2_max_regs(CF, SHARED_SM)) k2_synth(DeviceJob job)
+template <class A, int FMT, int S, int CF>
+__global__ void __maxnreg__(k2_max_regs(CF)) k2_synth(DeviceJob job)
 {
     typedef K2Geom<CF> G;
     constexpr int T = G::kThreads;
@@ -565,8 +563,8 @@ __device__ __forceinline__ void lean_run(const LeanSmem &sm, const uint4 *rows4,
         store_run<A, FMT, SR>(dst, acc);
 }
 
-template <int FMT, int S, bool SHARED_SM, int NB>
-__global__ void __maxnreg__(k2_max_regs(0, SHARED_SM)) k2_lean(DeviceJob job)
+template <int FMT, int S, int NB>
+__global__ void __maxnreg__(k2_max_regs(0)) k2_lean(DeviceJob job)
 {
     typedef AccF32x2 A;
     constexpr int T = kK2Threads;
@@ -597,9 +595,7 @@ __global__ void __maxnreg__(k2_max_regs(0, SHARED_SM)) k2_lean(DeviceJob job)
     const int lane = tid & 31;
     const uint32_t cthr_mask = job.force_wrap_path ? 0u : kCthrMask;
     constexpr int kBytesPer8 = (FMT == 16) ? 32 : (FMT == 8) ? 16 : 2;
-    // the next channel's state slot is prefetched too - except in the register-capped build, where the four
-    // extra live registers cost more than the load latency (measured: 4.61 -> 4.26 ms at 112 registers)
-    constexpr bool PF = kLeanPrefetchState && !SHARED_SM;
+    constexpr bool PF = kLeanPrefetchState; // the next channel's state slot is prefetched too (measured: 4.14 -> 4.06 ms)
 
     for (;;) {
         unsigned int unit = 0;
@@ -669,16 +665,16 @@ __global__ void __maxnreg__(k2_max_regs(0, SHARED_SM)) k2_lean(DeviceJob job)
     }
 }
 
-template <int FMT, int S, bool SHARED_SM = false, int NB = 0>
+template <int FMT, int S, int NB = 0>
 static cudaError_t launch_lean(const DeviceJob &job, cudaStream_t stream)
 {
     const size_t smem = lean_smem_bytes(job.max_active);
-    cudaError_t err = set_attr_once<k2_lean<FMT, S, SHARED_SM, NB>>(cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lean_smem_bytes(kMaxChan));
+    cudaError_t err = set_attr_once<k2_lean<FMT, S, NB>>(cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lean_smem_bytes(kMaxChan));
     if (err != cudaSuccess)
         return err;
     const long long warps_per_block = kK2Threads / 32;
     const int blocks = (int)std::min<long long>(std::max(1, job.sm_count), ((long long)job.n_units + warps_per_block - 1) / warps_per_block);
-    k2_lean<FMT, S, SHARED_SM, NB><<<blocks, kK2Threads, smem, stream>>>(job);
+    k2_lean<FMT, S, NB><<<blocks, kK2Threads, smem, stream>>>(job);
     return cudaGetLastError();
 }
 
@@ -739,20 +735,20 @@ __global__ void __launch_bounds__(128) k2_generic(DeviceJob job)
     }
 }
 
-template <class A, int FMT, int S, int CF, bool SHARED_SM = false>
+template <class A, int FMT, int S, int CF>
 static cudaError_t launch_tuned_a(const DeviceJob &job, cudaStream_t stream)
 {
     constexpr int T = K2Geom<CF>::kThreads;
     const size_t smem = kSmemLut + kSmemNegw + (size_t)std::max(1, job.max_active) * K2Geom<CF>::kStride;
     // the most this instantiation can ever ask for (CF = 2 only runs with <= kFloatWideMaxChan channels)
     constexpr size_t smem_max = kSmemLut + kSmemNegw + (size_t)(CF == 2 ? kFloatWideMaxChan : kMaxChan) * K2Geom<CF>::kStride;
-    cudaError_t err = set_attr_once<k2_synth<A, FMT, S, CF, SHARED_SM>>(cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+    cudaError_t err = set_attr_once<k2_synth<A, FMT, S, CF>>(cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     if (err != cudaSuccess)
         return err;
     const long long units = job.n_units;
     const long long warps_per_block = T / 32;
     const int blocks = (int)std::min<long long>(std::max(1, job.sm_count), (units + warps_per_block - 1) / warps_per_block);
-    k2_synth<A, FMT, S, CF, SHARED_SM><<<blocks, T, smem, stream>>>(job);
+    k2_synth<A, FMT, S, CF><<<blocks, T, smem, stream>>>(job);
     return cudaGetLastError();
 }
 
@@ -768,15 +764,11 @@ static cudaError_t launch_tuned(const DeviceJob &job, cudaStream_t stream)
     }
     if (job.accum == 1 && job.lean) {
         if (S == 32 && job.lin_nb == 2)
-            return launch_lean<FMT, 32, false, 2>(job, stream);
+            return launch_lean<FMT, 32, 2>(job, stream);
         if (S == 32 && job.lin_nb == 4)
-            return launch_lean<FMT, 32, false, 4>(job, stream);
-        if (S == 32 && job.shared_sm)
-            return launch_lean<FMT, 32, true>(job, stream);
+            return launch_lean<FMT, 32, 4>(job, stream);
         return launch_lean<FMT, S>(job, stream);
     }
-    if (S == 32 && job.accum == 1 && job.shared_sm)
-        return launch_tuned_a<AccF32x2, FMT, 32, 0, true>(job, stream);
     return job.accum == 1 ? launch_tuned_a<AccF32x2, FMT, S, 0>(job, stream)
                           : launch_tuned_a<AccWide, FMT, S, 0>(job, stream);
 }
@@ -792,21 +784,6 @@ static cudaError_t launch_generic(const DeviceJob &job, cudaStream_t stream)
     else
         k2_generic<FMT, false><<<blocks, threads, 0, stream>>>(job);
     return cudaGetLastError();
-}
-
-// Is there a build of the synthesis kernel for this job that leaves room for the next call's chain kernel?
-bool synth_has_shared_sm_build(const DeviceJob &job, SynthKernel which)
-{
-    if (which != SynthKernel::Tuned32)
-        return false;
-    // Double carrier: none.  Measured with a 112-register build of the 512-thread kernel (16 bytes of
-    // spills): its block fills the SM's shared memory (230 of 227 KiB - 1 KiB), so no chain block fits beside
-    // it at 13 channels, and where one does, the carrier chains - 3.7x the work of the code chains, and
-    // stretched ~3x when they share an SM - would outlast the synthesis kernel.  Serial 7.43 ms per step,
-    // "overlapped" 7.80 ms.
-    if (job.carrier_float)
-        return false;
-    return job.accum == 1;
 }
 
 cudaError_t launch_synth(const DeviceJob &job, SynthKernel which, cudaStream_t stream)

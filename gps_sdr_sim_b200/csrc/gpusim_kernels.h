@@ -42,7 +42,6 @@ struct DeviceJob {
     int32_t q;               // aligned layout: chunks per code period
     int32_t n_units;         // work units (32 chunks each) of the tuned kernel
     int32_t carrier_float;   // 1: FLOAT_CARR_PHASE host (double carrier phase), 0: integer carrier
-    int32_t shared_sm;       // 1: K2 build that leaves registers for the next call's K1 (see k2_max_regs)
     int32_t lean;            // 1: integer carrier runs k2_lean (default), 0: the round-1 k2_synth (kept as a cross-check)
     int32_t lin_nb;          // > 0: low chip rate - runs that qualify take synth_lin with this many chip boundaries (2 or 4)
     double lin_rinv;         // synth_lin: job-wide estimate of 1 / (f_code*delt)
@@ -65,8 +64,6 @@ enum class SynthKernel { Tuned32 = 0, Tuned16 = 1, Generic = 2 };
 cudaError_t launch_chain(const DeviceJob &job, ChainAlgo algo, cudaStream_t stream);
 // K2: samples -> bytes
 cudaError_t launch_synth(const DeviceJob &job, SynthKernel which, cudaStream_t stream);
-// true when launch_synth has a build for this job that can share the SM with the next call's chain kernel
-bool synth_has_shared_sm_build(const DeviceJob &job, SynthKernel which);
 // dynamic shared memory the tuned kernel needs for a given max_active (0 if it cannot run)
 size_t synth_smem_bytes(int max_active, int threads);
 int synth_threads();

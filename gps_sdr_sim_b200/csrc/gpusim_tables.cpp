@@ -132,15 +132,40 @@ uint32_t gpusim_pack_nav_bits(const unsigned long *dwrd, int32_t n_dwrd, int32_t
 
 // N executions of the FLOAT_CARR_PHASE carrier update (gpssim.c:2245-2250) in O(carrier cycles)
 // instead of O(N): the same exact binade walk the device uses, on the host.
-double gpusim_advance_carrier_f64(double carr_phase, double f_carr, double delt, int32_t n_samples)
+} // extern "C"
+
+namespace {
+inline double advance_carrier(double carr_phase, double f_carr, double delt, int32_t n_samples)
 {
     const volatile double d = f_carr * delt;
     if (n_samples <= 0 || d == 0.0)
         return carr_phase;
     auto nothing = [](int, double, int) {};
     const double x0 = carr_phase * 512.0, d512 = (double)d * 512.0;
-    gpusim::ChainTabHost tab;
-    return gpusim::carrier_chain(x0, d512, n_samples, 1 << 30, tab, nothing) / 512.0;
+    return (d512 < 0.0 ? gpusim::phase_chain<-1>(x0, d512, 512.0, n_samples, 1 << 30, nothing)
+                       : gpusim::phase_chain<1>(x0, d512, 512.0, n_samples, 1 << 30, nothing)) / 512.0;
+}
+#if defined(__x86_64__) && defined(__GNUC__)
+// The walk is a chain of fused multiply-adds.  Built for plain x86-64 (the reference's flags) every one of them
+// is a call into libm's software fma; with the FMA3 instructions of every CPU a B200 host can have it is one
+// instruction - same single rounding, same value.  (Explicit fma() calls only: -ffp-contract=off still keeps the
+// compiler from fusing any a*b+c on its own.)
+__attribute__((target("fma"))) double advance_carrier_fma3(double carr_phase, double f_carr, double delt, int32_t n_samples)
+{
+    return advance_carrier(carr_phase, f_carr, delt, n_samples);
+}
+#endif
+} // namespace
+
+extern "C" {
+double gpusim_advance_carrier_f64(double carr_phase, double f_carr, double delt, int32_t n_samples)
+{
+#if defined(__x86_64__) && defined(__GNUC__)
+    static const bool has_fma = __builtin_cpu_supports("fma");
+    if (has_fma)
+        return advance_carrier_fma3(carr_phase, f_carr, delt, n_samples);
+#endif
+    return advance_carrier(carr_phase, f_carr, delt, n_samples);
 }
 
 } // extern "C"

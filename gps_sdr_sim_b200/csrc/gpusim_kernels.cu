@@ -464,7 +464,19 @@ __global__ void __maxnreg__(k2_max_regs(CF)) k2_synth(DeviceJob job)
 // shared memory: [carrier table 64 KB][chip windows 33*34*8][lane table][state 16 B x channels x threads]
 // ------------------------------------------------------------------------------------
 constexpr size_t kSmemWin64 = ((size_t)kCaPrns * kCaWinBytes + 32 * sizeof(uint32_t) + 15) & ~(size_t)15;
-constexpr uint32_t kLeanStride = 16u * (uint32_t)kK2Threads;
+// Geometry of the lean kernel: threads per block, samples per run, register cap.  512 x 32 x 128 is what ships;
+// the macros exist for tools/build_variant.py experiments (e.g. 640 threads x runs of 24 x 96 registers).
+#ifndef GS_LEAN_THREADS
+#define GS_LEAN_THREADS GS_K2_THREADS
+#endif
+#ifndef GS_LEAN_S
+#define GS_LEAN_S 32
+#endif
+#ifndef GS_LEAN_REGS
+#define GS_LEAN_REGS 128
+#endif
+constexpr int kLeanThreads = GS_LEAN_THREADS;
+constexpr uint32_t kLeanStride = 16u * (uint32_t)kLeanThreads;
 #ifndef GS_LEAN_UNROLL
 #define GS_LEAN_UNROLL 1
 #endif
@@ -542,6 +554,9 @@ __device__ __forceinline__ void lean_run(const LeanSmem &sm, const uint4 *rows4,
                     synth_lin<A, SR, (NB > 0 ? NB : 1)>(acc, x, phs, d, r0.z, st.w, win, c0, job.lin_rinv, sm.lut, lane_off);
                 else
                     synth_fast_g<A, SR>(acc, x, phs, d, r0.z, st.w, win, magic, sm.lut, lane_off);
+                // (8- and 4-byte stores at a 16-byte lane stride are 2- and 4-way bank conflicts: 6.6 % of the
+                // kernel's shared-memory wavefronts, ncu r02.  One 16-byte store of the whole slot has none, but
+                // keeps the gain word alive across the run: spills, 4.06 -> 4.15 ms.  The conflicts are cheaper.)
                 sts_f64(sa, x);
                 sts_u32(sa + 8u, phs);
             } else {
@@ -564,10 +579,10 @@ __device__ __forceinline__ void lean_run(const LeanSmem &sm, const uint4 *rows4,
 }
 
 template <int FMT, int S, int NB>
-__global__ void __maxnreg__(k2_max_regs(0)) k2_lean(DeviceJob job)
+__global__ void __maxnreg__(GS_LEAN_REGS) k2_lean(DeviceJob job)
 {
     typedef AccF32x2 A;
-    constexpr int T = kK2Threads;
+    constexpr int T = kLeanThreads;
     extern __shared__ __align__(16) unsigned char smem[];
     LeanSmem sm;
     uint64_t *lut = reinterpret_cast<uint64_t *>(smem);
@@ -669,12 +684,12 @@ template <int FMT, int S, int NB = 0>
 static cudaError_t launch_lean(const DeviceJob &job, cudaStream_t stream)
 {
     const size_t smem = lean_smem_bytes(job.max_active);
-    cudaError_t err = set_attr_once<k2_lean<FMT, S, NB>>(cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lean_smem_bytes(kMaxChan));
+    cudaError_t err = set_attr_once<k2_lean<FMT, S, NB>>(cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(lean_smem_bytes(kMaxChan), 232448));
     if (err != cudaSuccess)
         return err;
-    const long long warps_per_block = kK2Threads / 32;
+    const long long warps_per_block = kLeanThreads / 32;
     const int blocks = (int)std::min<long long>(std::max(1, job.sm_count), ((long long)job.n_units + warps_per_block - 1) / warps_per_block);
-    k2_lean<FMT, S, NB><<<blocks, kK2Threads, smem, stream>>>(job);
+    k2_lean<FMT, S, NB><<<blocks, kLeanThreads, smem, stream>>>(job);
     return cudaGetLastError();
 }
 
@@ -767,7 +782,7 @@ static cudaError_t launch_tuned(const DeviceJob &job, cudaStream_t stream)
             return launch_lean<FMT, 32, 2>(job, stream);
         if (S == 32 && job.lin_nb == 4)
             return launch_lean<FMT, 32, 4>(job, stream);
-        return launch_lean<FMT, S>(job, stream);
+        return launch_lean<FMT, (S == 32 ? GS_LEAN_S : S)>(job, stream);
     }
     return job.accum == 1 ? launch_tuned_a<AccF32x2, FMT, S, 0>(job, stream)
                           : launch_tuned_a<AccWide, FMT, S, 0>(job, stream);

@@ -22,7 +22,7 @@ import oracle_lib  # noqa: E402
 rng = np.random.default_rng(1)
 
 N_CHOICES = [104, 1000, 4096, 10000, 65536, 100000, 123456, 123457, 200000, 208000, 250000, 260000,
-             260008, 400000, 1000000, 2000000]
+             260008, 400000, 840000, 1000000, 1640000, 2000000]
 BUDGET = 1.2e8     # sample-channels per case: keeps the oracle at a fraction of a second
 
 
@@ -70,7 +70,7 @@ def random_table():
     opts = {}
     if rng.random() < 0.5:
         opts = dict([(("force_slow", 1), ("layout", 1), ("accum", 0), ("chain_replay", 1), ("force_generic", 1),
-                      ("pipeline", 2), ("pipeline", 0), ("float_geom", 1))[int(rng.integers(8))]])
+                      ("pipeline", 2), ("pipeline", 1), ("float_geom", 1), ("lowrate", 0), ("lean", 0))[int(rng.integers(10))]])
         if "layout" in opts and rng.random() < 0.5:
             opts["chunk"] = int(rng.choice([64, 96, 128, 1024, 4096]))
     return t, opts, note

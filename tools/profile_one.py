@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """One short K1+K2 job for ncu.
 
-    python tools/profile_one.py [fmt] [accum] [epochs] [chunk] [carrier_mode] [pipeline]     synthetic rows
+    python tools/profile_one.py [fmt] [accum] [epochs] [chunk] [carrier_mode] [pipeline] [samples_per_epoch] [channels]   synthetic rows
     python tools/profile_one.py --table <table.npz> [pipeline]                                 a saved EpochTable
     python tools/profile_one.py --scenario <name> [pipeline]                                   rows recorded from the reference host
 
@@ -32,7 +32,9 @@ else:
     chunk = int(argv[3]) if len(argv) > 3 else 0
     mode = int(argv[4]) if len(argv) > 4 else 0
     pipeline = int(argv[5]) if len(argv) > 5 else 0
-    t = gs.synthetic_table(E, 260000, 13, fmt, carrier_mode=mode)
+    n_samples = int(argv[6]) if len(argv) > 6 else 260000
+    channels = int(argv[7]) if len(argv) > 7 else 13
+    t = gs.synthetic_table(E, n_samples, channels, fmt, carrier_mode=mode)
 E = t.n_epochs
 out = torch.empty(E * t.epoch_bytes, dtype=torch.uint8, device="cuda")
 with gs.GpuSim.for_table(t) as sim:

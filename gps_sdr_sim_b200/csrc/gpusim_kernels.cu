@@ -508,7 +508,7 @@ struct LeanSmem {
 template <int FMT, int SR, bool UNI, bool PF, int NB>
 __device__ __forceinline__ void lean_run(const LeanSmem &sm, const uint4 *rows4, const int nc, const int ncw,
                                          const bool live, const unsigned mask, const uint32_t lane_off,
-                                         const uint32_t cthr_mask, const DeviceJob &job, uint8_t *dst)
+                                         const uint32_t cthr_mask, const double lin_rinv, uint8_t *dst)
 {
     typedef AccF32x2 A;
     A::acc_t acc[SR];
@@ -551,7 +551,7 @@ __device__ __forceinline__ void lean_run(const LeanSmem &sm, const uint4 *rows4,
             const bool all_lin = NB > 0 && !any_wrap && __all_sync(UNI ? 0xffffffffu : __activemask(), lin_ok(c0, NB));
             if (!any_wrap) {
                 if (all_lin)
-                    synth_lin<A, SR, (NB > 0 ? NB : 1)>(acc, x, phs, d, r0.z, st.w, win, c0, job.lin_rinv, sm.lut, lane_off);
+                    synth_lin<A, SR, (NB > 0 ? NB : 1)>(acc, x, phs, d, r0.z, st.w, win, c0, lin_rinv, sm.lut, lane_off);
                 else
                     synth_fast_g<A, SR>(acc, x, phs, d, r0.z, st.w, win, magic, sm.lut, lane_off);
                 // (8- and 4-byte stores at a 16-byte lane stride are 2- and 4-way bank conflicts: 6.6 % of the
@@ -665,15 +665,15 @@ __global__ void __maxnreg__(GS_LEAN_REGS) k2_lean(DeviceJob job)
 
             if (uni) {
                 for (int i = 0; i < full_w; i++)
-                    lean_run<FMT, S, true, PF, NB>(sm, rows4, nc, ncw, true, mask, lane_off, cthr_mask, job,
+                    lean_run<FMT, S, true, PF, NB>(sm, rows4, nc, ncw, true, mask, lane_off, cthr_mask, NB > 0 ? job.lin_rinv : 0.0,
                                            outp + (size_t)i * (S / 8) * kBytesPer8);
             } else {
                 for (int i = 0; i < full_w; i++)
-                    lean_run<FMT, S, false, PF, NB>(sm, rows4, nc, ncw, i < full, mask, lane_off, cthr_mask, job,
+                    lean_run<FMT, S, false, PF, NB>(sm, rows4, nc, ncw, i < full, mask, lane_off, cthr_mask, NB > 0 ? job.lin_rinv : 0.0,
                                             outp + (size_t)i * (S / 8) * kBytesPer8);
             }
             for (int i = 0; i < tail_w; i++)
-                lean_run<FMT, 8, false, PF, NB>(sm, rows4, nc, ncw, i < tail8, mask, lane_off, cthr_mask, job,
+                lean_run<FMT, 8, false, PF, NB>(sm, rows4, nc, ncw, i < tail8, mask, lane_off, cthr_mask, NB > 0 ? job.lin_rinv : 0.0,
                                         outp + ((size_t)full * (S / 8) + i) * kBytesPer8);
         }
         __syncwarp();

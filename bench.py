@@ -234,19 +234,23 @@ def pick_device(local_rank: int, world: int, n_visible: int) -> int:
     return local_rank
 
 
-def link_rate_gbs(torch, n_bytes: int = 256 << 20) -> float:
-    """this GPU's pinned device-to-host rate right now (all ranks measure at the same time)"""
+def link_rate_gbs(torch, dist, window_s: float = 0.4, n_bytes: int = 64 << 20) -> float:
+    """This GPU's pinned device-to-host rate while EVERY rank copies: all ranks start together (barrier) and keep
+    copying for the same wall-clock window, so each one sees the contention of the full set for the whole
+    measurement (a fixed number of copies would let the fast links finish early and flatter the slow ones)."""
     src = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
     dst = torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
     dst.copy_(src, non_blocking=True)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(3):
-        dst.copy_(src, non_blocking=True)
-    e1.record()
+    dist.barrier()
     torch.cuda.synchronize()
-    return 3 * n_bytes / 1e9 / (e0.elapsed_time(e1) / 1e3)
+    t0 = time.perf_counter()
+    copied = 0
+    while time.perf_counter() - t0 < window_s:
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        copied += n_bytes
+    return copied / 1e9 / (time.perf_counter() - t0)
 
 
 def isolated_call_ms(gs, torch, table, device, repeats: int = 4):
@@ -321,6 +325,21 @@ def ncu_live(table_path: str, timeout_s: int = 240):
     return out
 
 
+class OneLineStdout:
+    """The driver reads ONE JSON line from stdout.  Libraries write there too (NCCL prints its version when the box
+    sets NCCL_DEBUG, torch.distributed warnings ...): while the benchmark runs, file descriptor 1 points at stderr;
+    emit() writes the line to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.write(self.real, (line + "\n").encode())
+
+
 def main_b200(args):
     import hashlib
 
@@ -328,6 +347,7 @@ def main_b200(args):
     import torch.distributed as dist
     import gps_sdr_sim_b200 as gs
 
+    out_line = OneLineStdout()
     rank, local_rank, world = rank_env()
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
@@ -417,23 +437,24 @@ def main_b200(args):
     share = count
     rates = None
     if world > 1:
-        mine = torch.tensor([link_rate_gbs(torch)], dtype=torch.float64, device="cuda")
+        mine = torch.tensor([link_rate_gbs(torch, dist)], dtype=torch.float64, device="cuda")
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
         rates = [float(r) for r in allr]
         total = count * world
-        shares = [max(1, min(count, int(total * r / sum(rates)))) for r in rates]
-        # epochs capped at one table per rank; what the caps cut off goes to the ranks with room, fastest first
-        left = total - sum(shares)
-        for i in sorted(range(world), key=lambda i: -rates[i]):
-            add = min(left, count - shares[i])
-            shares[i] += add
-            left -= add
+        # a rank may get more than one table's worth of epochs (it then runs the scenario again from the start):
+        # the work is N x 2999 epochs whichever way it is cut
+        shares = [max(1, int(total * r / sum(rates))) for r in rates]
+        shares[max(range(world), key=lambda i: rates[i])] += total - sum(shares)
         share = shares[rank]
-    e2e_table = table.slice(0, share)
+    reps, rest = divmod(share, count)
+    e2e_tables = [table] * reps + ([table.slice(0, rest)] if rest else [])
     host_out = torch.empty(share * eb, dtype=torch.uint8, pin_memory=True)
     def e2e_step():
-        sim.generate_epochs(e2e_table, out_ptr=host_out.data_ptr(), out_capacity=host_out.numel())
+        off = 0
+        for tb in e2e_tables:
+            sim.generate_epochs(tb, out_ptr=host_out.data_ptr() + off, out_capacity=host_out.numel() - off)
+            off += tb.n_epochs * eb
     for _ in range(min(2, args.warmup)):
         e2e_step()
     barrier()
@@ -446,8 +467,9 @@ def main_b200(args):
     e2e_ok = None
     if rank == 0:
         try:
+            last = (share - 1) % count          # scenario epoch the last generated epoch is
             e2e_ok = bool(hashlib.sha256(host_out[(share - 1) * eb:share * eb].numpy().tobytes()).digest() ==
-                          hashlib.sha256(oracle_lib.generate(table, share - 1, 1).tobytes()).digest())
+                          hashlib.sha256(oracle_lib.generate(table, last, 1).tobytes()).digest())
         except Exception:  # noqa: BLE001
             pass
     sampler.stop()
@@ -533,7 +555,7 @@ def main_b200(args):
                 sim.close()
             line["configs"] = other_configs(gs, torch, device)
         line["cpu_baseline"] = cpu_baseline(45.0 if world == 1 else 10.0)
-        print(json.dumps(line), flush=True)
+        out_line.emit(json.dumps(line))
 
     sim.close()
     if world > 1:

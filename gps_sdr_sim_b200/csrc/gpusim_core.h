@@ -48,6 +48,10 @@
 #ifndef GS_PACK_FMA
 #define GS_PACK_FMA 1
 #endif
+//   GS_CARRIER_WRAP_PRED  double carrier: the wrap of the carrier phase as a predicated add (see carrier_step_signed)
+#ifndef GS_CARRIER_WRAP_PRED
+#define GS_CARRIER_WRAP_PRED 1
+#endif
 
 namespace gpusim {
 
@@ -938,6 +942,20 @@ GS_HD double carrier_step_signed(double cph, const double dc)
 {
     cph = dadd(cph, dc);
 #ifdef __CUDA_ARCH__
+#if GS_CARRIER_WRAP_PRED
+    // The wrap as ONE predicated add behind an INTEGER test of the upper word: ISETP + @P DADD, two
+    // instructions and a 21-cycle recurrence.  (Round 1 wrote it as "add -512 or -0.0", the addend's upper
+    // word selected with shift + LOP3: the compiler then re-creates the addend's zero lower word for every
+    // sample - four instructions, 26 cycles; plain C makes it DADD + DSETP + two FSEL.)  Rising: cph in
+    // [0,1024), so cph >= 512 <=> upper word >= 0x40800000.  Falling: cph in (-512,512) and never -0.0 (an
+    // exact zero sum is +0.0 in round-to-nearest), so cph < 0 <=> sign bit.
+    if (kFalling)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %1, 0;\n\t@p bra SKIP;\n\tadd.rn.f64 %0, %0, 0d4080000000000000;\nSKIP:\n\t}"
+            : "+d"(cph) : "r"(__double2hiint(cph)));
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %1, 0x40800000;\n\t@p bra SKIP;\n\tadd.rn.f64 %0, %0, 0dC080000000000000;\nSKIP:\n\t}"
+            : "+d"(cph) : "r"(__double2hiint(cph)));
+#else
     // The wrap as "add -512 or -0.0" chosen by an INTEGER test of the upper word: one compare and one
     // select on the ALU pipe and one DADD, instead of the compiler's DADD + DSETP + two FSEL (it
     // computes cph -+ 512 unconditionally and selects both halves).  Rising: cph in [0,1024), so
@@ -948,6 +966,7 @@ GS_HD double carrier_step_signed(double cph, const double dc)
         cph = __dadd_rn(cph, __hiloint2double(hi < 0 ? 0x40800000 : 0, 0));
     else
         cph = __dadd_rn(cph, __hiloint2double(hi >= 0x40800000 ? (int)0xC0800000u : (int)0x80000000u, 0));
+#endif
 #else
     if (kFalling) {
         if (cph < 0.0)

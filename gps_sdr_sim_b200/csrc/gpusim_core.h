@@ -605,7 +605,10 @@ GS_HD double phase_chain_tab(double x, const double d, const double M, const int
     // beyond it makes the chain take the segment, one genuine step (the one that crosses the binade edge, wraps,
     // or walks the untabulated binades) and open the next segment.  On the device every lane of a warp thus
     // emits checkpoint j at the same point of the program - one coalesced store per warp - whatever the number
-    // of trips each lane needed to get there, and no trip is spent on stopping at a checkpoint.
+    // of trips each lane needed to get there, and no trip is spent on stopping at a checkpoint.  The trip is
+    // branch-free on purpose: the binades too small to jump in go through the same instructions with r = 0 (a
+    // shortcut for them - no lookup, no floor - makes the lanes of a warp take different paths: K1 0.21 -> 0.24 ms,
+    // 0.66 -> 0.80 ms with carrier chains, measured).
     int n = 0, wraps = 0, k = 0;
     double delta = 0.0, kf = 0.0;
     auto open_segment = [&]() {

@@ -31,16 +31,13 @@
 //                       multiply-add on the FMA pipe, instead of shift + LOP3 (both ALU).  4.303 -> 4.240 ms.
 //   GS_CHIP_GAIN_INT    integer carrier: the chip sign flips the sign bit of the fp32 gain (the broadcast operand
 //                       of FFMA2) instead of the top bit of the carrier phase.  No gain (4.315 ms): off.
-//   GS_CHIP_GAIN_FLOAT  double carrier: same; the table lookup then depends on the carrier chain only, one
-//                       instruction less on the kernel's critical path.  7.74 -> 7.16 ms: on.
+//   (double carrier: the chip sign always rides on the gain - the table lookup then depends on the carrier chain
+//                       only, one instruction less on the kernel's critical path: 7.74 -> 7.16 ms in round 1.)
 #ifndef GS_ADDR_IMAD
 #define GS_ADDR_IMAD 1
 #endif
 #ifndef GS_CHIP_GAIN_INT
 #define GS_CHIP_GAIN_INT 0
-#endif
-#ifndef GS_CHIP_GAIN_FLOAT
-#define GS_CHIP_GAIN_FLOAT 1
 #endif
 //   GS_PACK_FMA         16/8-bit output from the fp32 accumulators: (acc+64)>>7 (and >>4 more for 8-bit) taken by ONE
 //                       round-down FFMA2 per sample (I and Q) and the bytes gathered with PRMT - 2 / 2.5 instructions
@@ -1023,26 +1020,20 @@ GS_HD typename A::tab_t lut_at_f(const typename A::tab_t *lut, uint32_t idx, uin
 #endif
 }
 
+// gbits: fp32 bits of dataBit*gain (kept in the thread's state: no conversion per run); c0 / magic: floor(x) and
+// 2^52 - floor(x) from floor_magic() (two FP64 adds instead of a conversion each way).  The chip sign goes onto
+// the gain: the table lookup depends on the carrier phase only.
 template <class A, int S, bool kFalling>
 GS_HD void synth_fast_f(typename A::acc_t (&acc)[S], ChanStateF &st, const double d, const double dc,
-                        const int signed_gain, const uint32_t win, const typename A::tab_t *lut,
+                        const uint32_t gbits, const uint32_t win, const double magic, const typename A::tab_t *lut,
                         const uint32_t lane_off)
 {
+    // (instantiated, never run, for the 64-bit integer accumulator: only AccF32x2 has a sign bit in its gain)
     double x = st.x, cph = st.cph;
-    const int c0 = (int)x;
-    const double magic = 4503599627370496.0 - (double)c0;
-    const typename A::gain_t g = A::make_gain(signed_gain);
-    // the window as a 64-bit value win << 9: shifted left by the chips advanced, bit 8 of the upper
-    // word is the current chip (bit 31 - adv of win) - one funnel shift per sample
-    const uint32_t wlo = win << 9, whi = win >> 23;
-    const uint32_t gb = A::gain_bits(signed_gain);
 #pragma unroll
     for (int j = 0; j < S; j++) {
-        const uint32_t adv = chips_since(x, magic);
-        if (A::kSignInGain && GS_CHIP_GAIN_FLOAT) // chip sign on the gain: the lookup depends on the carrier phase only
-            A::mad_s(acc[j], lut_at_f<A>(lut, carrier_index(cph), 0u, lane_off), gb ^ ((win << adv) & 0x80000000u));
-        else
-            A::mad(acc[j], lut_at_f<A>(lut, carrier_index(cph), funnel_l(wlo, whi, adv), lane_off), g);
+        const uint32_t t = j == 0 ? win : win << chips_since(x, magic);
+        A::mad_s(acc[j], lut_at_f<A>(lut, carrier_index(cph), 0u, lane_off), gbits ^ (t & 0x80000000u));
         x = dadd(x, d);
         cph = carrier_step_signed<kFalling>(cph, dc);
     }

@@ -155,7 +155,7 @@ size_t synth_smem_bytes(int max_active, int threads)
 // that the per-channel address update is a single integer add.  With T threads per block, channel k,
 // thread t:
 //   integer carrier: k*16T + t*8 : code phase f64 ; + 8T : (carrier phase << 7, meta)
-//   double carrier : k*24T + t*8 : code phase f64 ; + 8T : 512*carr_phase f64 ; + 16T : meta
+//   double carrier : k*24T + t*8 : code phase f64 ; + 8T : 512*carr_phase f64 ; + 16T : (meta, fp32 bits of dataBit*gain)
 // meta = icode | bitk<<8 | (dataBit*gain)<<16.
 template <class A>
 struct K2Smem {
@@ -276,9 +276,10 @@ __device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows
         // addresses (6.17 -> 5.99 ms); the integer-carrier kernel is issue bound and LOSES 1.4 % with that
         // shape (4.17 -> 4.23 ms: the window loads move in front of the branch on the vote), so it keeps the plain form.
         int c0 = 0;
+        double magic = 0.0;
         bool wrap = false;
         if (CF) {
-            c0 = (int)x; // x = 0 on idle lanes
+            magic = floor_magic(x, c0); // floor(x) and 2^52 - floor(x): two FP64 adds, no F2I / I2F (x = 0 on idle lanes)
             wrap = act && c0 >= (int)(r0.w & cthr_mask);
         } else if (act) {
             wrap = (int)x >= (int)(r0.w & cthr_mask);
@@ -309,14 +310,15 @@ __device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows
                 ChanStateF st;
                 st.x = x;
                 st.cph = lds_f64(sa + G::kSecond);
-                const uint32_t meta = lds_u32(sa + G::kMeta);
                 // rising and falling carrier phase have their own loops (one wrap test each)
                 if (!any_wrap) {
+                    const uint32_t gbits = lds_u32(sa + G::kMeta + 4u); // fp32 bits of dataBit*gain
                     if (dc < 0.0)
-                        synth_fast_f<A, SR, true>(acc, st, d, dc, meta_sgain(meta), win_f, sm.lut, lane_off);
+                        synth_fast_f<A, SR, true>(acc, st, d, dc, gbits, win_f, magic, sm.lut, lane_off);
                     else
-                        synth_fast_f<A, SR, false>(acc, st, d, dc, meta_sgain(meta), win_f, sm.lut, lane_off);
+                        synth_fast_f<A, SR, false>(acc, st, d, dc, gbits, win_f, magic, sm.lut, lane_off);
                 } else {
+                    const uint32_t meta = lds_u32(sa + G::kMeta);
                     const uint4 r1 = rows4[2 * k + 1];
                     st.icode = meta_icode(meta);
                     st.bitk = meta_bitk(meta);
@@ -324,7 +326,8 @@ __device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows
                         synth_wrap_f<A, SR, true>(acc, st, d, dc, (int32_t)r1.y, r1.z, win_f, sm.lut, lane_off);
                     else
                         synth_wrap_f<A, SR, false>(acc, st, d, dc, (int32_t)r1.y, r1.z, win_f, sm.lut, lane_off);
-                    sts_u32(sa + G::kMeta, pack_meta(st.icode, st.bitk, data_sign(r1.z, st.bitk) * (int32_t)r1.y));
+                    const int sg = data_sign(r1.z, st.bitk) * (int32_t)r1.y;
+                    sts_u32x2(sa + G::kMeta, pack_meta(st.icode, st.bitk, sg), A::gain_bits(sg));
                 }
                 sts_f64(sa, st.x);
                 sts_f64(sa + G::kSecond, st.cph);
@@ -425,7 +428,7 @@ __global__ void __maxnreg__(k2_max_regs(CF)) k2_synth(DeviceJob job)
                     sts_u32x2(sa + G::kSecond, r.ph0s + (uint32_t)n0 * (uint32_t)r.steps, meta);
                 } else {
                     sts_f64(sa + G::kSecond, job.ck_c[ck]);
-                    sts_u32(sa + G::kMeta, meta);
+                    sts_u32x2(sa + G::kMeta, meta, A::gain_bits(data_sign(r.nav_bits, bitk) * r.gain));
                 }
             }
 

@@ -194,13 +194,16 @@ void emu_run_f(const Tables &T, const DevRow *rows, const double *dcs, int nc, C
         acc[j] = A::init();
     for (int k = 0; k < nc; k++) {
         const DevRow &r = rows[k];
-        const bool wrap = (int)st[k].x >= row_cthr(r) || force_wrap;
+        int c0;
+        const double magic = floor_magic(st[k].x, c0);
+        const bool wrap = c0 >= row_cthr(r) || force_wrap;
         const uint32_t *nw = T.negw.data() + (size_t)row_prn(r) * kCaWords;
         if (!wrap) {
+            const uint32_t gbits = A::gain_bits(meta_sgain(meta[k])); // the device keeps these bits next to meta
             if (dcs[k] < 0.0)
-                synth_fast_f<A, SR, true>(acc, st[k], r.d, dcs[k], meta_sgain(meta[k]), chip_window(nw, (int)st[k].x), lut, lane_off);
+                synth_fast_f<A, SR, true>(acc, st[k], r.d, dcs[k], gbits, chip_window(nw, c0), magic, lut, lane_off);
             else
-                synth_fast_f<A, SR, false>(acc, st[k], r.d, dcs[k], meta_sgain(meta[k]), chip_window(nw, (int)st[k].x), lut, lane_off);
+                synth_fast_f<A, SR, false>(acc, st[k], r.d, dcs[k], gbits, chip_window(nw, c0), magic, lut, lane_off);
         } else {
             st[k].icode = meta_icode(meta[k]);
             st[k].bitk = meta_bitk(meta[k]);

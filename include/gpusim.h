@@ -151,10 +151,10 @@ int gpusim_generate_epochs_to_sink(gpusim_ctx *ctx, const gpusim_epoch_table *ta
  * samples on the GPU: upload once, then generate any epoch sub-range
  * [first_epoch, first_epoch+n_epochs) of the uploaded table into device memory.
  * `stream` is a cudaStream_t (NULL = the library's own stream); the call is
- * asynchronous with respect to the host when a stream is given.  Calls issued
- * back to back are pipelined: the output of call i is complete when `stream`
- * reaches the point after call i, but the code-phase chain kernel of call i+1
- * already runs (on a library stream) beside the synthesis kernel of call i.
+ * asynchronous with respect to the host when a stream is given: the output of
+ * call i is complete when `stream` reaches the point after call i.  (Option
+ * "pipeline" >= 1 moves the code-phase chain kernel of a call to a library
+ * stream, where it may start while the previous call's synthesis kernel drains.)
  */
 int gpusim_upload_table(gpusim_ctx *ctx, const gpusim_epoch_table *table);
 int gpusim_generate_device(gpusim_ctx *ctx, int32_t first_epoch, int32_t n_epochs,
@@ -174,8 +174,11 @@ int64_t gpusim_debug_guard_violations(gpusim_ctx *ctx);
  *   "force_generic" 1 = always use the generic exact kernel
  *   "force_slow" 1 = always take the wrap-checking inner loop
  *   "direct_first_mb", "direct_mb" sub-batch sizes (MiB) of gpusim_generate_epochs (default 16, 64)
- *   "pipeline" 1 = (default) overlap the chain kernel with the previous call's synthesis kernel
- *              when the epoch is long enough for that to pay, 0 = never, 2 = whenever possible
+ *   "pipeline" 0 = (default) chain kernel in front of its synthesis kernel on the caller's stream; 1 = on the
+ *              library's chain stream when the previous call is still running; 2 = always on that stream
+ *   "lean"     integer carrier: 1 = (default) k2_lean, 0 = the round-1 kernel k2_synth (cross-check)
+ *   "lowrate"  1 = (default) tables with >= 8 samples per chip take the linear-model path for chip boundaries, 0 = never
+ *   "accum", "layout", "chain_replay"  cross-check variants, see DESIGN.md 5
  *   "float_geom" FLOAT hosts: 0 = (default) 512-thread kernel when <= 13 channels are active, else the
  *              384-thread one; 1 = always the 384-thread kernel */
 int gpusim_set_option(gpusim_ctx *ctx, const char *key, int64_t value);

@@ -444,11 +444,8 @@ def main_b200(args):
         total = count * world
         # a rank may get more than one table's worth of epochs (it then runs the scenario again from the start):
         # the work is N x 2999 epochs whichever way it is cut
-        shares = [max(1, int(total * r / sum(rates))) for r in rates]
-        shares[max(range(world), key=lambda i: rates[i])] += total - sum(shares)
-        share = shares[rank]
-    reps, rest = divmod(share, count)
-    e2e_tables = [table] * reps + ([table.slice(0, rest)] if rest else [])
+        share = link_aware_shares(total, rates)[rank]
+    e2e_tables = [table if n == count else table.slice(0, n) for n in repeats_of(share, count)]
     host_out = torch.empty(share * eb, dtype=torch.uint8, pin_memory=True)
     def e2e_step():
         off = 0

@@ -15,7 +15,7 @@ import torch.multiprocessing as mp
 
 import oracle_lib
 from conftest import load_golden
-from gps_sdr_sim_b200.shard import batches, epoch_range
+from gps_sdr_sim_b200.shard import batches, epoch_range, link_aware_shares, repeats_of
 
 
 def test_epoch_range_partitions_exactly():
@@ -34,6 +34,21 @@ def test_batches_cover_range_in_order():
     assert list(batches(5, 0, 4)) == []
     assert list(batches(5, 10, 4)) == [(5, 4), (9, 4), (13, 2)]
     assert list(batches(0, 8, 8)) == [(0, 8)]
+
+
+def test_link_aware_shares_sum_and_follow_the_rates():
+    # the 8-GPU box of profiles/r02_pcie_8gpu.md: four links at 11.6 GB/s, four at 18.5
+    rates = [11.6] * 4 + [18.5] * 4
+    sh = link_aware_shares(8 * 2999, rates)
+    assert sum(sh) == 8 * 2999 and min(sh) >= 1
+    assert sh[4] > 2999 > sh[0]                                  # the fast links take more than one table's worth
+    assert abs(sh[0] / sh[5] - 11.6 / 18.5) < 0.01
+    assert link_aware_shares(10, [1.0, 1.0]) == [5, 5]
+    assert sum(link_aware_shares(7, [1.0, 1e-6, 1.0])) == 7
+    with pytest.raises(ValueError):
+        link_aware_shares(1, [1.0, 1.0])
+    assert repeats_of(3686, 2999) == [2999, 687] and repeats_of(2999, 2999) == [2999] and repeats_of(5, 2999) == [5]
+    assert sum(repeats_of(3 * 2999 + 1, 2999)) == 3 * 2999 + 1
 
 
 def _worker(rank, world, port, name, tmp):

@@ -346,6 +346,7 @@ def main_b200(args):
     import torch
     import torch.distributed as dist
     import gps_sdr_sim_b200 as gs
+    from gps_sdr_sim_b200.shard import link_aware_shares, repeats_of
 
     out_line = OneLineStdout()
     rank, local_rank, world = rank_env()

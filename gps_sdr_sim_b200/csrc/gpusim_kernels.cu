@@ -502,6 +502,23 @@ __device__ __forceinline__ void sts_u32x4(uint32_t a, uint32_t v0, uint32_t v1, 
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v0), "r"(v1), "r"(v2), "r"(v3));
 }
 
+__device__ __forceinline__ uint4 ldg_u32x4(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+// The row of the next channel through an explicit ld.global: with a plain C++ load ptxas re-derived the shared-window
+// base (S2UR + UMOV + ULEA) in every trip of the channel loop and spilled 28 bytes; with this form it does neither.
+#ifndef GS_LEAN_ASM_ROW
+#define GS_LEAN_ASM_ROW 1
+#endif
+#if GS_LEAN_ASM_ROW
+#define GS_LEAN_ROW_LOAD(p) ldg_u32x4(p)
+#else
+#define GS_LEAN_ROW_LOAD(p) (*(p))
+#endif
+
 struct LeanSmem {
     const uint64_t *lut; // replicated carrier table (float2 entries)
     uint32_t win_s;      // shared-window address of the chip-window table
@@ -523,7 +540,7 @@ __device__ __forceinline__ void lean_run(const LeanSmem &sm, const uint4 *rows4,
     // software pipeline over channels: row and state of channel k+1 are in flight while channel k is generated
     uint4 r0n = make_uint4(0, 0, 0, 0), stn = make_uint4(0, 0, 0, 0);
     if (UNI || (live && nc > 0)) {
-        r0n = rows4[0];
+        r0n = GS_LEAN_ROW_LOAD(rows4);
         if (PF)
             stn = lds_u32x4(sa);
     }
@@ -535,7 +552,7 @@ __device__ __forceinline__ void lean_run(const LeanSmem &sm, const uint4 *rows4,
         if (!PF && act)
             st = lds_u32x4(sa);
         if (UNI ? (k + 1 < ncw) : (live && k + 1 < nc)) {
-            r0n = rows4[2 * k + 2];
+            r0n = GS_LEAN_ROW_LOAD(rows4 + 2 * k + 2);
             if (PF)
                 stn = lds_u32x4(sa + kLeanStride);
         }
@@ -808,6 +825,9 @@ cudaError_t launch_synth(const DeviceJob &job, SynthKernel which, cudaStream_t s
 {
     if (job.n_epochs == 0)
         return cudaSuccess;
+#ifdef GS_ONLY_LEAN8 // development builds (SASS inspection): one instantiation, compiles in seconds
+    return launch_lean<8, 32>(job, stream);
+#else
 #define GS_DISPATCH(FMTV)                                                        \
     if (which == SynthKernel::Tuned32) return launch_tuned<FMTV, 32>(job, stream); \
     if (which == SynthKernel::Tuned16) return launch_tuned<FMTV, 16>(job, stream); \
@@ -816,6 +836,7 @@ cudaError_t launch_synth(const DeviceJob &job, SynthKernel which, cudaStream_t s
     if (job.fmt == 8) { GS_DISPATCH(8) }
     GS_DISPATCH(1)
 #undef GS_DISPATCH
+#endif
 }
 
 } // namespace gpusim

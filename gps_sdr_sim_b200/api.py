@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 from . import build as _build
-from .table import CEpochTable, EpochTable, epoch_bytes
+from .table import NAV_FRAME, CEpochTable, EpochTable, epoch_bytes
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # GPUSIM_LIB: load another build of the same library (kernel experiments); default = the in-tree build
@@ -48,6 +48,7 @@ EXPORTS = (
     "gpusim_upload_table", "gpusim_generate_device", "gpusim_get_timing", "gpusim_set_option",
     "gpusim_carrier_lut", "gpusim_ca_code", "gpusim_pack_nav_bits", "gpusim_advance_carrier_f64",
     "gpusim_host_alloc", "gpusim_host_free", "gpusim_debug_guard_violations",
+    "gpusim_nav_build", "gpusim_nav_read",
 )
 
 
@@ -101,6 +102,10 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.gpusim_host_free.argtypes = [vp]
     lib.gpusim_debug_guard_violations.restype = i64
     lib.gpusim_debug_guard_violations.argtypes = [vp]
+    lib.gpusim_nav_build.restype = ctypes.c_int
+    lib.gpusim_nav_build.argtypes = [vp, vp, i32]
+    lib.gpusim_nav_read.restype = ctypes.c_int
+    lib.gpusim_nav_read.argtypes = [vp, i32, i32, vp]
     lib.gpusim_advance_carrier_f64.restype = ctypes.c_double
     lib.gpusim_advance_carrier_f64.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_double, i32]
     _lib = lib
@@ -220,6 +225,18 @@ class GpuSim:
         """out_ptr: 16-byte aligned device pointer (e.g. torch tensor .data_ptr()); stream: cudaStream_t."""
         self._check(self._lib.gpusim_generate_device(self._ctx, first_epoch, n_epochs, out_ptr, out_capacity,
                                                      stream))
+
+    # ---- navigation data words on the device (SURVEY 8 f4) -------------------------------------
+    def nav_build(self, frames: np.ndarray) -> None:
+        """gpusim_nav_build: frames is a NAV_FRAME array, one element per generateNavMsg() call (gpssim.c:1467-1547)."""
+        f = np.ascontiguousarray(frames, dtype=NAV_FRAME)
+        self._check(self._lib.gpusim_nav_build(self._ctx, f.ctypes.data, f.size))
+
+    def nav_read(self, first_frame: int, n_frames: int) -> np.ndarray:
+        """The 60 data words (chan->dwrd) of frames [first_frame, first_frame + n_frames), as built on the device."""
+        out = np.empty((n_frames, 60), dtype=np.uint32)
+        self._check(self._lib.gpusim_nav_read(self._ctx, first_frame, n_frames, out.ctypes.data))
+        return out
 
     def guard_violations(self) -> int:
         """gpusim_debug_guard_violations: 0 = nothing wrote outside the context's device buffers (needs GPUSIM_GUARD=1)."""

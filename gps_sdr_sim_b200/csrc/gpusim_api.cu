@@ -68,6 +68,11 @@ struct gpusim_ctx {
     int sm_count = 148;
     int min_chunk = 128;
 
+    // navigation frames built on the device (gpusim_nav_build): requests and their 60 words each
+    NavFrame *d_nav_req = nullptr;
+    uint32_t *d_nav_words = nullptr;
+    int nav_capacity = 0, nav_frames = 0;
+
     // output
     uint8_t *d_out = nullptr; // lazily: max_batch_epochs * epoch_bytes
     uint8_t *h_stage[2] = {nullptr, nullptr};
@@ -551,8 +556,11 @@ int gpusim_upload_table(gpusim_ctx *ctx, const gpusim_epoch_table *t)
     if (t->n_epochs < 0 || t->n_epochs > ctx->cfg.max_batch_epochs)
         return fail(ctx, GPUSIM_ERR_CAPACITY, "table has %d epochs, context capacity is %d", t->n_epochs, ctx->cfg.max_batch_epochs);
     const bool cf = ctx->cfg.carrier_mode == GPUSIM_CARRIER_FLOAT;
-    if (!t->prn || !t->f_code || !t->code_phase || !t->icode || !t->nav_bits || !t->gain)
-        return fail(ctx, GPUSIM_ERR_ARG, "tables need prn, f_code, code_phase, icode, nav_bits, gain");
+    if (!t->prn || !t->f_code || !t->code_phase || !t->icode || !t->gain)
+        return fail(ctx, GPUSIM_ERR_ARG, "tables need prn, f_code, code_phase, icode, gain");
+    const bool nav_ref = t->nav_bits == nullptr; // data bits come from device-built frames (gpusim_nav_build)
+    if (nav_ref && (!t->nav_frame || !t->iword || !t->ibit))
+        return fail(ctx, GPUSIM_ERR_ARG, "tables need nav_bits, or nav_frame + iword + ibit");
     if (!cf && (!t->carr_phasestep || !t->carr_phase))
         return fail(ctx, GPUSIM_ERR_ARG, "integer-carrier tables need carr_phasestep and carr_phase");
     if (cf && (!t->f_carr || !t->carr_phase_f))
@@ -598,9 +606,19 @@ int gpusim_upload_table(gpusim_ctx *ctx, const gpusim_epoch_table *t)
                 ctx->h_cph0[(size_t)e * kMaxChan + nc] = cp * 512.0;
             }
             o.gain = t->gain[r];
-            o.nav_bits = t->nav_bits[r];
             o.icode0 = (uint16_t)t->icode[r];
             o.flags = 0;
+            if (nav_ref) {
+                // (chan[i].iword, chan[i].ibit) of gpssim.c:1343-1344 inside frame nav_frame; resolved by k0_navbits
+                if (t->nav_frame[r] < 0 || t->nav_frame[r] >= ctx->nav_frames || t->iword[r] < 0 || t->iword[r] >= kNavWords ||
+                    t->ibit[r] < 0 || t->ibit[r] >= 30)
+                    return fail(ctx, GPUSIM_ERR_ARG, "epoch %d slot %d: nav_frame %d (have %d), iword %d, ibit %d out of range", e, i,
+                                t->nav_frame[r], ctx->nav_frames, t->iword[r], t->ibit[r]);
+                o.nav_bits = ((uint32_t)t->nav_frame[r] << 11) | ((uint32_t)t->iword[r] << 5) | (uint32_t)t->ibit[r];
+                o.flags |= kRowNavRef;
+            } else {
+                o.nav_bits = t->nav_bits[r];
+            }
             if (o.gain < 0 || o.gain > kTunedMaxGain) {
                 o.flags |= kRowNeedsGeneric;
                 ctx->needs_generic = true;
@@ -641,9 +659,57 @@ int gpusim_upload_table(gpusim_ctx *ctx, const gpusim_epoch_table *t)
             GS_CUDA(ctx, cudaMemcpyAsync(ctx->d_dc, ctx->h_dc, rows * sizeof(double), cudaMemcpyHostToDevice, ctx->s_compute));
             GS_CUDA(ctx, cudaMemcpyAsync(ctx->d_cph0, ctx->h_cph0, rows * sizeof(double), cudaMemcpyHostToDevice, ctx->s_compute));
         }
+        if (nav_ref)
+            GS_CUDA(ctx, launch_navbits(ctx->d_rows, (int)rows, ctx->d_nav_words, ctx->s_compute));
         GS_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
     }
     ctx->n_uploaded = t->n_epochs;
+    return GPUSIM_OK;
+}
+
+int gpusim_nav_build(gpusim_ctx *ctx, const gpusim_nav_frame *frames, int32_t n_frames)
+{
+    static_assert(sizeof(gpusim_nav_frame) == sizeof(NavFrame), "gpusim_nav_frame is the device layout");
+    if (!ctx || n_frames < 0 || (n_frames > 0 && !frames))
+        return GPUSIM_ERR_ARG;
+    if ((uint32_t)n_frames > kNavRefMaxFrames)
+        return fail(ctx, GPUSIM_ERR_CAPACITY, "%d navigation frames, at most %u per call", n_frames, kNavRefMaxFrames);
+    GS_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    {
+        // rows of an earlier upload may still be resolved against the old words
+        const int rc_drain = drain(ctx);
+        if (rc_drain != GPUSIM_OK)
+            return rc_drain;
+    }
+    if (n_frames > ctx->nav_capacity) {
+        // grows geometrically; the old buffers stay in the context's allocation list until gpusim_destroy
+        const int cap = std::max(n_frames, std::max(64, 2 * ctx->nav_capacity));
+        GS_CUDA(ctx, dev_alloc(ctx, &ctx->d_nav_req, (size_t)cap * sizeof(NavFrame)));
+        GS_CUDA(ctx, dev_alloc(ctx, &ctx->d_nav_words, (size_t)cap * kNavWords * sizeof(uint32_t)));
+        ctx->nav_capacity = cap;
+    }
+    ctx->nav_frames = 0;
+    if (n_frames > 0) {
+        GS_CUDA(ctx, cudaMemcpyAsync(ctx->d_nav_req, frames, (size_t)n_frames * sizeof(NavFrame), cudaMemcpyHostToDevice, ctx->s_compute));
+        GS_CUDA(ctx, launch_navmsg(ctx->d_nav_req, n_frames, ctx->d_nav_words, ctx->s_compute));
+        GS_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute)); // `frames` is the caller's again
+    }
+    ctx->nav_frames = n_frames;
+    return GPUSIM_OK;
+}
+
+int gpusim_nav_read(gpusim_ctx *ctx, int32_t first, int32_t n, uint32_t *dwrd)
+{
+    if (!ctx || (n > 0 && !dwrd))
+        return GPUSIM_ERR_ARG;
+    if (first < 0 || n < 0 || first > ctx->nav_frames || n > ctx->nav_frames - first)
+        return fail(ctx, GPUSIM_ERR_ARG, "frames first=%d n=%d outside the %d built", first, n, ctx->nav_frames);
+    if (n == 0)
+        return GPUSIM_OK;
+    GS_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    GS_CUDA(ctx, cudaMemcpyAsync(dwrd, ctx->d_nav_words + (size_t)first * kNavWords, (size_t)n * kNavWords * sizeof(uint32_t),
+                                 cudaMemcpyDeviceToHost, ctx->s_compute));
+    GS_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
     return GPUSIM_OK;
 }
 

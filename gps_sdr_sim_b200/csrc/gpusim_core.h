@@ -209,6 +209,9 @@ GS_HD int row_prn(const DevRow &r) { return (int)(r.cthr_prn >> 10); }
 
 constexpr uint32_t kRowNeedsGeneric = 1u;
 constexpr uint32_t kRowTieInLinRange = 2u; // f_code*delt is an exact half-ulp tie in one of the binades [2^5, 2^10) (synth_lin)
+constexpr uint32_t kRowNavRef = 4u;        // nav_bits still holds a reference into the device-built data words (k0_navbits resolves it)
+// reference to a position in a device-built frame: frame << 11 | iword << 5 | ibit
+constexpr uint32_t kNavRefMaxFrames = 1u << 21;
 constexpr int kTunedMaxGain = 255; // 16 ch * 250 * 255 + 64 < 2^20: the accumulator fields below hold it
 
 // ---- accumulator policies of the tuned kernel -----------------------------------------
@@ -1250,6 +1253,112 @@ GS_HD void generic_sample(GenericChan *ch, int nc, const int16_t *sin512, const 
     }
     i16 = (int)(short)((i_acc + 64) >> 7);
     q16 = (int)(short)((q_acc + 64) >> 7);
+}
+
+// =====================================================================================
+// K0 - navigation data words (replaces generateNavMsg, gpssim.c:1467-1547, and its parity
+// routine computeChecksum, gpssim.c:693-756, for hosts that hand the library subframes instead of data bits).
+//
+// A frame is what ONE generateNavMsg() call leaves in chan->dwrd[60]: the last subframe of the previous
+// frame (words 0..9) followed by subframes 1..5 (words 10..59) of the 30 s that start at g0.  Every word is
+// the 24 source bits from eph2sbf() plus, in the hand-over word (word 2 of a subframe), the TOW count of the
+// NEXT subframe and, in word 3 of subframe 1, the week number - then the six parity bits of IS-GPS-200
+// 20.3.5.2, chained through the two last bits of the word before.  Words 2 and 10 of a subframe solve their
+// bits 23/24 so that their own two last bits come out zero, which is why every subframe starts from a
+// previous word of 0 and the six subframes of a frame can be built independently of each other (the
+// reference's refresh copies words 50..59 of the previous frame, which end in such a word).
+// =====================================================================================
+constexpr int kNavWordsPerSubframe = 10; // N_DWRD_SBF, gpssim.h:30
+constexpr int kNavSubframes = 6;         // N_SBF + 1,  gpssim.h:27,:33
+constexpr int kNavWords = kNavWordsPerSubframe * kNavSubframes; // N_DWRD
+
+GS_HD uint32_t nav_popc(uint32_t v)
+{
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__popc(v);
+#else
+    return (uint32_t)__builtin_popcount(v);
+#endif
+}
+
+// One transmitted word from its source word.  src: bits 29..6 = d1..d24, bits 31/30 = D29*/D30* of the word
+// sent before.  Returns D1..D30 in bits 29..0 (data bits inverted when D30* is set, parity in bits 5..0).
+// solve_tail: word 2 / word 10 - bits d23, d24 are not information; choose them so that D29 = D30 = 0.
+GS_HD uint32_t nav_word(uint32_t src, bool solve_tail)
+{
+    // rows of the parity matrix over d1..d24 (bit 29 = d1), IS-GPS-200 table 20-XIV; `star` = which of
+    // D29* (1) / D30* (0) enters the row
+    const uint32_t rows[6] = {0x3B1F3480u, 0x1D8F9A40u, 0x2EC7CD00u, 0x1763E680u, 0x2BB1F340u, 0x0B7A89C0u};
+    const uint32_t star[6] = {1u, 0u, 1u, 0u, 0u, 1u};
+    const uint32_t prev[2] = {(src >> 30) & 1u, (src >> 31) & 1u}; // [0] = D30*, [1] = D29*
+    uint32_t d = src & 0x3FFFFFC0u;
+    if (solve_tail) {
+        // d24 (bit 6) is in row D29 but d23 (bit 7) is not; both are in row D30: fix D29 with d24 first
+        if ((prev[star[4]] + nav_popc(rows[4] & d)) & 1u)
+            d ^= 1u << 6;
+        if ((prev[star[5]] + nav_popc(rows[5] & d)) & 1u)
+            d ^= 1u << 7;
+    }
+    uint32_t w = prev[0] ? d ^ 0x3FFFFFC0u : d;
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+        w |= ((prev[star[r]] + nav_popc(rows[r] & d)) & 1u) << (5 - r);
+    return w & 0x3FFFFFFFu;
+}
+
+// Ten words of one subframe.  src10: the subframe's source words (chan->sbf[isbf], gpssim.h:174); tow_next:
+// TOW count written into the hand-over word; week10: < 0, or the 10-bit week number for word 3 (subframe 1).
+GS_HD void nav_subframe(const uint32_t *src10, uint32_t tow_next, int week10, uint32_t *out10)
+{
+    uint32_t before = 0u;
+#pragma unroll 1
+    for (int i = 0; i < kNavWordsPerSubframe; i++) {
+        uint32_t sw = src10[i];
+        if (i == 2 && week10 >= 0)
+            sw |= ((uint32_t)week10 & 0x3FFu) << 20; // gpssim.c:1527
+        if (i == 1)
+            sw |= (tow_next & 0x1FFFFu) << 13;        // gpssim.c:1531, :1493
+        sw |= before << 30;                            // D29*, D30* (upper bits of `before` fall off)
+        before = nav_word(sw, i == 1 || i == 9);
+        out10[i] = before;
+    }
+}
+
+// The 32 data bits a row starts with: bit 31 = (dwrd[iword] >> (29 - ibit)) & 1, then the bits the sample
+// loop walks to (gpssim.c:2223-2236); past word 59 they read 0.  Same contract as gpusim_pack_nav_bits().
+GS_HD uint32_t nav_row_bits(const uint32_t *dwrd60, int iword, int ibit)
+{
+    uint32_t out = 0u;
+    int w = iword, b = ibit;
+    for (int k = 0; k < 32; k++) {
+        if (w >= 0 && w < kNavWords)
+            out |= ((dwrd60[w] >> (29 - b)) & 1u) << (31 - k);
+        if (++b == 30) {
+            b = 0;
+            w++;
+        }
+    }
+    return out;
+}
+
+// Device layout of one frame request (what crosses the ABI as gpusim_nav_frame): 64 words.
+struct NavFrame {
+    uint32_t sbf[5][kNavWordsPerSubframe]; // source words of subframes 1..5
+    uint32_t first[kNavWordsPerSubframe];  // source words of the frame's words 0..9 (a subframe 5)
+    uint32_t tow_first;                    // TOW count for those
+    uint32_t tow;                          // TOW count of the frame start; subframe s (1..5) carries tow + s
+    uint32_t week10;                       // transmission week number mod 1024
+    uint32_t reserved;
+};
+static_assert(sizeof(NavFrame) == 256, "NavFrame layout");
+
+// subframe s of frame f (s = 0: the leading subframe 5, s = 1..5: subframes 1..5) -> out[s*10 .. s*10+9]
+GS_HD void nav_build_subframe(const NavFrame &f, int s, uint32_t *dwrd60)
+{
+    if (s == 0)
+        nav_subframe(f.first, f.tow_first, -1, dwrd60);
+    else
+        nav_subframe(f.sbf[s - 1], f.tow + (uint32_t)s, s == 1 ? (int)(f.week10 & 0x3FFu) : -1, dwrd60 + s * kNavWordsPerSubframe);
 }
 
 } // namespace gpusim

@@ -39,6 +39,53 @@ static cudaError_t set_attr_once(cudaFuncAttribute attr, int value)
 }
 
 // ------------------------------------------------------------------------------------
+// K0 - navigation data words on the device
+// ------------------------------------------------------------------------------------
+// one thread per (frame, subframe): 10 words chained through their parity; the six subframes of a frame
+// do not depend on each other (nav_subframe)
+__global__ void __launch_bounds__(128) k0_navmsg(const NavFrame *frames, int n_frames, uint32_t *dwrd)
+{
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = gid / kNavSubframes;
+    if (f >= n_frames)
+        return;
+    nav_build_subframe(frames[f], gid - f * kNavSubframes, dwrd + (size_t)f * kNavWords);
+}
+
+// one thread per uploaded row: rows that came with (frame, iword, ibit) instead of data bits get their 32
+// data bits from the frame's words
+__global__ void __launch_bounds__(128) k0_navbits(DevRow *rows, int n_rows, const uint32_t *dwrd)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows)
+        return;
+    const uint32_t flags = rows[r].flags;
+    if (!(flags & kRowNavRef))
+        return;
+    const uint32_t ref = rows[r].nav_bits;
+    rows[r].nav_bits = nav_row_bits(dwrd + (size_t)(ref >> 11) * kNavWords, (int)((ref >> 5) & 63u), (int)(ref & 31u));
+    rows[r].flags = (uint16_t)(flags & ~kRowNavRef);
+}
+
+cudaError_t launch_navmsg(const NavFrame *frames, int n_frames, uint32_t *dwrd, cudaStream_t stream)
+{
+    if (n_frames <= 0)
+        return cudaSuccess;
+    const int threads = 128, total = n_frames * kNavSubframes;
+    k0_navmsg<<<(total + threads - 1) / threads, threads, 0, stream>>>(frames, n_frames, dwrd);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_navbits(DevRow *rows, int n_rows, const uint32_t *dwrd, cudaStream_t stream)
+{
+    if (n_rows <= 0)
+        return cudaSuccess;
+    const int threads = 128;
+    k0_navbits<<<(n_rows + threads - 1) / threads, threads, 0, stream>>>(rows, n_rows, dwrd);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------
 // K1
 // ------------------------------------------------------------------------------------
 // binade constants of one chain (phase_chain_tab) in shared memory: [field][binade][lane], conflict-free

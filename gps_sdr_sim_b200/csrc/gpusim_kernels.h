@@ -60,6 +60,9 @@ __host__ __device__ inline size_t ck_elems(int n_epochs, int kc) { return (size_
 enum class ChainAlgo { Jump = 0, Replay = 1 };
 enum class SynthKernel { Tuned32 = 0, Tuned16 = 1, Generic = 2 };
 
+// K0: data words of n_frames navigation frames (60 each); data bits of the rows that reference them
+cudaError_t launch_navmsg(const NavFrame *frames, int n_frames, uint32_t *dwrd, cudaStream_t stream);
+cudaError_t launch_navbits(DevRow *rows, int n_rows, const uint32_t *dwrd, cudaStream_t stream);
 // K1: exact code-phase checkpoints for every (epoch, active channel, chunk)
 cudaError_t launch_chain(const DeviceJob &job, ChainAlgo algo, cudaStream_t stream);
 // K2: samples -> bytes

@@ -23,11 +23,19 @@ _COLUMNS = (
     ("carr_phase", np.uint32), ("f_carr", np.float64), ("carr_phase_f", np.float64),
 )
 _DUMP_EXTRA = (("iword", np.int32), ("ibit", np.int32))
+# rows may reference device-built navigation frames instead of carrying their data bits
+_NAV_REF = (("nav_frame", np.int32), ("iword", np.int32), ("ibit", np.int32))
+
+# struct gpusim_nav_frame (include/gpusim.h): the input of one generateNavMsg() call, 256 bytes
+NAV_FRAME = np.dtype([("sbf", np.uint32, (5, 10)), ("first", np.uint32, (10,)), ("tow_first", np.uint32),
+                      ("tow", np.uint32), ("wn", np.uint32), ("reserved", np.uint32)])
+assert NAV_FRAME.itemsize == 256
 
 
 class CEpochTable(ctypes.Structure):
     """ctypes mirror of struct gpusim_epoch_table."""
-    _fields_ = [("n_epochs", ctypes.c_int32)] + [(name, ctypes.c_void_p) for name, _ in _COLUMNS]
+    _fields_ = ([("n_epochs", ctypes.c_int32)] + [(name, ctypes.c_void_p) for name, _ in _COLUMNS] +
+                [(name, ctypes.c_void_p) for name, _ in _NAV_REF])
 
 
 def epoch_bytes(samples_per_epoch: int, data_format: int) -> int:
@@ -48,6 +56,7 @@ class EpochTable:
     data_format: int = SC16                # -b
     carrier_mode: int = CARRIER_INT
     cols: dict = field(default_factory=dict)   # name -> np.ndarray [n_epochs, 16]
+    nav_by_reference: bool = False             # rows carry nav_frame / iword / ibit, not nav_bits (gpusim_nav_build first)
 
     @property
     def n_epochs(self) -> int:
@@ -65,7 +74,9 @@ class EpochTable:
 
     def validate(self) -> None:
         n = self.n_epochs
-        for name, dt in _COLUMNS:
+        for name, dt in _COLUMNS + (_NAV_REF if self.nav_by_reference else ()):
+            if name not in self.cols:
+                raise ValueError(f"column {name} is missing")
             a = self.cols[name]
             if a.dtype != dt or a.shape != (n, MAX_CHAN) or not a.flags.c_contiguous:
                 raise ValueError(f"column {name}: want C-contiguous {dt} [{n},{MAX_CHAN}]")
@@ -73,10 +84,17 @@ class EpochTable:
     def slice(self, first: int, count: int) -> "EpochTable":
         """Rows of epochs [first, first+count) - epochs are independent given their rows."""
         cols = {k: np.ascontiguousarray(v[first:first + count]) for k, v in self.cols.items()}
-        return EpochTable(self.samples_per_epoch, self.delt, self.data_format, self.carrier_mode, cols)
+        return EpochTable(self.samples_per_epoch, self.delt, self.data_format, self.carrier_mode, cols, self.nav_by_reference)
 
     def with_format(self, data_format: int) -> "EpochTable":
-        return EpochTable(self.samples_per_epoch, self.delt, data_format, self.carrier_mode, self.cols)
+        return EpochTable(self.samples_per_epoch, self.delt, data_format, self.carrier_mode, self.cols, self.nav_by_reference)
+
+    def with_nav_references(self, nav_frame: np.ndarray) -> "EpochTable":
+        """The same rows, their data bits to be taken on the device from frame nav_frame[e, slot] of the last
+        GpuSim.nav_build() at (iword, ibit) - needs the iword / ibit columns a host dump carries."""
+        cols = dict(self.cols)
+        cols["nav_frame"] = np.ascontiguousarray(nav_frame, dtype=np.int32)
+        return EpochTable(self.samples_per_epoch, self.delt, self.data_format, self.carrier_mode, cols, True)
 
     def as_c(self) -> CEpochTable:
         """The ctypes struct; keeps referencing self.cols, so keep `self` alive."""
@@ -85,6 +103,10 @@ class EpochTable:
         c.n_epochs = self.n_epochs
         for name, _ in _COLUMNS:
             setattr(c, name, self.cols[name].ctypes.data)
+        if self.nav_by_reference:
+            c.nav_bits = None
+            for name, _ in _NAV_REF:
+                setattr(c, name, self.cols[name].ctypes.data)
         return c
 
     def max_active(self) -> int:

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GPUSIM_ABI_VERSION 1
+#define GPUSIM_ABI_VERSION 2 /* 2: gpusim_epoch_table grew nav_frame / iword / ibit; gpusim_nav_build */
 
 /* gpssim.h:16  MAX_CHAN - channel slots per epoch row */
 #define GPUSIM_MAX_CHAN 16
@@ -89,6 +89,11 @@ typedef struct gpusim_config {
  *   f_carr         chan[i].f_carr                        (gpssim.c:1327)   FLOAT mode
  *   carr_phase_f   chan[i].carr_phase (double) at epoch start              FLOAT mode
  *
+ *   nav_frame, iword, ibit   (optional) instead of nav_bits: the row's
+ *                  data bits are taken on the device from frame nav_frame of the last
+ *                  gpusim_nav_build() call, starting at (chan[i].iword, chan[i].ibit)
+ *                  (gpssim.c:1343-1345).  Used when nav_bits is NULL.
+ *
  * Arrays of the other carrier mode may be NULL.  The library copies what it
  * needs before returning; no pointer is retained.
  */
@@ -104,7 +109,42 @@ typedef struct gpusim_epoch_table {
     const uint32_t *carr_phase;
     const double *f_carr;
     const double *carr_phase_f;
+    const int32_t *nav_frame;
+    const int32_t *iword;
+    const int32_t *ibit;
 } gpusim_epoch_table;
+
+/*
+ * SURVEY 8 f4 - navigation data words built on the device.
+ *
+ * One gpusim_nav_frame is the input of ONE generateNavMsg() call of the reference
+ * (gpssim.c:1467-1547): the satellite's five subframes as eph2sbf() left them in
+ * chan->sbf (gpssim.c:490-665: 24 source bits per word in bits 29..6, no TOW count,
+ * no week number, no parity), and the time the frame starts at.  The device adds the
+ * TOW counts and the week number and computes the parity of all 60 words
+ * (computeChecksum, gpssim.c:693-756), i.e. what the reference keeps in chan->dwrd[60]
+ * (gpssim.h:175):
+ *
+ *   words  0.. 9  subframe 5 of the frame before: built from `first` with TOW count
+ *                 tow_first.  generateNavMsg(init=1) builds them from chan->sbf[4] and tow
+ *                 (gpssim.c:1484-1503): first = sbf[4], tow_first = tow.  On a refresh
+ *                 (init=0, gpssim.c:1504-1511) the reference copies words 50..59 of the
+ *                 previous frame: first = the PREVIOUS call's sbf[4] (it differs from the
+ *                 current one after an ephemeris-set switch, gpssim.c:2318-2330),
+ *                 tow_first = previous tow + 5.
+ *   words 10..59  subframes 1..5 from sbf[0..4] with TOW counts tow+1 .. tow+5, week number
+ *                 wn in word 3 of subframe 1 (gpssim.c:1517-1543).
+ *
+ *   tow = ((unsigned long)g0.sec)/6, wn = g0.week%1024 with g0 as at gpssim.c:1476-1481.
+ */
+typedef struct gpusim_nav_frame {
+    uint32_t sbf[5][10];
+    uint32_t first[10];
+    uint32_t tow_first;
+    uint32_t tow;
+    uint32_t wn;
+    uint32_t reserved; /* 0 */
+} gpusim_nav_frame;
 
 /* Ordered output sink: called with consecutive byte ranges of the output file
  * (what fwrite(..., fp) received at gpssim.c:2276/:2283/:2287).  Non-zero aborts. */
@@ -161,6 +201,16 @@ int gpusim_generate_device(gpusim_ctx *ctx, int32_t first_epoch, int32_t n_epoch
                            void *out_device, size_t out_capacity, void *stream);
 
 int gpusim_get_timing(const gpusim_ctx *ctx, gpusim_timing *out);
+
+/*
+ * Replaces generateNavMsg() + computeChecksum() (gpssim.c:1467-1547, :693-756) for n_frames
+ * frames: their 60 data words each are built on the device and stay there; tables uploaded or
+ * generated afterwards may reference them by index (nav_frame / iword / ibit).  A later call
+ * replaces the whole set.  gpusim_nav_read() copies words of frames [first, first+n) back
+ * (60 uint32 per frame) - for tests and for hosts that want to cross-check chan->dwrd.
+ */
+int gpusim_nav_build(gpusim_ctx *ctx, const gpusim_nav_frame *frames, int32_t n_frames);
+int gpusim_nav_read(gpusim_ctx *ctx, int32_t first_frame, int32_t n_frames, uint32_t *dwrd);
 
 /* Test facility.  A context created with GPUSIM_GUARD=1 in the environment places every device buffer it
  * owns (rows, code-phase checkpoints, work counters, its own output buffer) between two 4 KiB poisoned guard

@@ -23,6 +23,13 @@
  *   GPUSIM_DRYRUN        1: record (and dump) rows, generate nothing, write nothing
  *   GPUSIM_HOST_THREADS  host threads for the row pre-pass (default: online CPUs, at most 16; 1 = the
  *                        reference's serial order of calls, nothing precomputed)
+ *   GPUSIM_NAV_DEVICE    1: navigation data words on the device.  Rows reference frames
+ *                        (one per generateNavMsg() call, rebuilt from chan[i].sbf by gpusim_nav_build)
+ *                        instead of carrying 32 data bits taken from chan[i].dwrd.
+ *   GPUSIM_NAV_CHECK     1 (with GPUSIM_NAV_DEVICE): read the device-built words back after every
+ *                        build and compare them with the host's chan[i].dwrd; a difference is fatal
+ *   GPUSIM_NAV_DUMP      path (with GPUSIM_NAV_DEVICE): every frame request (struct gpusim_nav_frame)
+ *                        followed by the 60 words the host's generateNavMsg() holds for it
  *
  * Host pre-pass.  Producing the rows is the reference's own code and stays
  * bit-identical; what changes is when and where it runs:
@@ -70,10 +77,28 @@ typedef struct
 	uint32_t *carr_phase;
 	double *f_carr;
 	double *carr_phase_f;
-	int32_t *iword; /* diagnostics only (dump) */
+	int32_t *iword; /* dump; GPUSIM_NAV_DEVICE: position of the row's first data bit in its frame */
 	int32_t *ibit;
 	double *carr_init; /* FLOAT hosts: carrier phase of a freshly allocated channel, or HOOK_CONTINUE */
+	/* GPUSIM_NAV_DEVICE: the navigation frames this batch's rows reference (index = nav_frame[row]) */
+	int32_t *nav_frame;
+	gpusim_nav_frame *frames;
+	uint32_t *frames_expect; /* GPUSIM_NAV_CHECK: chan[i].dwrd[60] as the host built it, per frame */
+	int n_frames, cap_frames;
 } cols_t;
+
+/* GPUSIM_NAV_DEVICE: what the shim remembers about the frame a channel slot is transmitting */
+typedef struct
+{
+	int active;              /* the slot held this PRN in the previous epoch */
+	int prn;
+	gpstime_t g0;            /* chan[i].g0 of the frame (gpssim.c:1478) */
+	uint32_t seen_sbf[5][N_DWRD_SBF]; /* chan[i].sbf as of the previous epoch: what the NEXT refresh's
+	                                     generateNavMsg(init=0) will read - the reference rebuilds the
+	                                     subframes of a new ephemeris set AFTER that call (gpssim.c:2300-2330) */
+	gpusim_nav_frame frame;  /* the current frame's request */
+	int batch_index;         /* its index in the current batch's frame list, -1 = not registered yet */
+} nav_slot_t;
 
 /* the reference's own functions (gpssim.c:789, :1253; external linkage, not declared in gpssim.h) */
 extern void computeRange(range_t *rho, ephem_t eph, ionoutc_t *ionoutc, gpstime_t g, double xyz[]);
@@ -173,6 +198,10 @@ struct gpusim_hook
 	long epochs_written; /* epochs delivered to the output file so far (what a failure report states) */
 	gpusim_config cfg;   /* what every worker creates its context with */
 	size_t epoch_bytes;  /* gpssim.c:2276/:2283/:2287 */
+	int nav_device, nav_check; /* GPUSIM_NAV_DEVICE, GPUSIM_NAV_CHECK */
+	FILE *nav_dump;            /* GPUSIM_NAV_DUMP */
+	nav_slot_t nav[MAX_CHAN];
+	long nav_frames_built;
 	int slots_ready;     /* page-locked ring buffers allocated (several GPUs; done by worker 0 once CUDA is up) */
 	double t_ctx;        /* wall clock [s] the slowest worker spent creating its context */
 };
@@ -226,6 +255,7 @@ static void cols_reserve(cols_t *c, int epochs)
 	c->iword = xrealloc(c->iword, rows * sizeof(int32_t));
 	c->ibit = xrealloc(c->ibit, rows * sizeof(int32_t));
 	c->carr_init = xrealloc(c->carr_init, rows * sizeof(double));
+	c->nav_frame = xrealloc(c->nav_frame, rows * sizeof(int32_t));
 	c->cap = epochs;
 }
 
@@ -234,6 +264,7 @@ static void cols_free(cols_t *c)
 	free(c->prn); free(c->f_code); free(c->code_phase); free(c->icode);
 	free(c->nav_bits); free(c->gain); free(c->carr_phasestep); free(c->carr_phase);
 	free(c->f_carr); free(c->carr_phase_f); free(c->iword); free(c->ibit); free(c->carr_init);
+	free(c->nav_frame); free(c->frames); free(c->frames_expect);
 	memset(c, 0, sizeof(*c));
 }
 
@@ -258,15 +289,21 @@ static int sink_fwrite(void *user, const void *bytes, size_t n)
 	return fwrite(bytes, 1, n, h->fp) == n ? 0 : 1;
 }
 
-static void table_of(const cols_t *c, gpusim_epoch_table *t)
+static void table_of(const cols_t *c, gpusim_epoch_table *t, int nav_device)
 {
 	memset(t, 0, sizeof(*t));
 	t->n_epochs = c->n;
+	if (nav_device)
+	{
+		t->nav_frame = c->nav_frame;
+		t->iword = c->iword;
+		t->ibit = c->ibit;
+	}
 	t->prn = c->prn;
 	t->f_code = c->f_code;
 	t->code_phase = c->code_phase;
 	t->icode = c->icode;
-	t->nav_bits = c->nav_bits;
+	t->nav_bits = nav_device ? NULL : c->nav_bits;
 	t->gain = c->gain;
 	t->carr_phasestep = c->carr_phasestep;
 	t->carr_phase = c->carr_phase;
@@ -586,7 +623,29 @@ static void *worker_main(void *arg)
 		s = &h->slots[seq % h->nslots];
 		pthread_mutex_unlock(&h->mu);
 
-		table_of(&s->rows, &t);
+		table_of(&s->rows, &t, h->nav_device);
+		if (h->nav_device)
+		{
+			/* generateNavMsg + computeChecksum for the frames of this batch, on this worker's GPU */
+			rc = gpusim_nav_build(w->ctx, s->rows.frames, s->rows.n_frames);
+			if (rc == GPUSIM_OK && h->nav_check)
+			{
+				uint32_t *got = malloc((size_t)(s->rows.n_frames > 0 ? s->rows.n_frames : 1) * N_DWRD * sizeof(uint32_t));
+				rc = got == NULL ? GPUSIM_ERR_ARG : gpusim_nav_read(w->ctx, 0, s->rows.n_frames, got);
+				if (rc == GPUSIM_OK && memcmp(got, s->rows.frames_expect, (size_t)s->rows.n_frames * N_DWRD * sizeof(uint32_t)) != 0)
+				{
+					free(got);
+					pipeline_fail(h, "GPUSIM_NAV_CHECK: device-built navigation words differ from generateNavMsg()", NULL);
+					return NULL;
+				}
+				free(got);
+			}
+			if (rc != GPUSIM_OK)
+			{
+				pipeline_fail(h, "building the navigation frames on the GPU failed", gpusim_last_error(w->ctx));
+				return NULL;
+			}
+		}
 		if (h->ndev == 1) /* one GPU: this thread is also the (ordered) writer, from the library's staging buffers */
 			rc = gpusim_generate_epochs_to_sink(w->ctx, &t, sink_fwrite, h);
 		else
@@ -641,6 +700,86 @@ static void *writer_main(void *arg)
 	}
 }
 
+/* ---- GPUSIM_NAV_DEVICE: frames instead of data bits ----------------------------- */
+/* the batch that is being filled starts without frames: every slot registers its frame again */
+static void nav_new_batch(gpusim_hook *h)
+{
+	int i;
+	h->batch.n_frames = 0;
+	for (i = 0; i < MAX_CHAN; i++)
+		h->nav[i].batch_index = -1;
+}
+
+static void nav_copy_sbf(uint32_t dst[5][N_DWRD_SBF], unsigned long src[5][N_DWRD_SBF])
+{
+	int a, b;
+	for (a = 0; a < 5; a++)
+		for (b = 0; b < N_DWRD_SBF; b++)
+			dst[a][b] = (uint32_t)src[a][b]; /* generateNavMsg reads them into an `unsigned` (gpssim.c:1473) */
+}
+
+/* Frame index (in the batch being filled) of what slot i transmits in this epoch.  A frame is one
+ * generateNavMsg() call: chan[i].g0 or the PRN changed since the previous epoch. */
+static int nav_frame_of(gpusim_hook *h, int i, channel_t *c)
+{
+	nav_slot_t *t = &h->nav[i];
+	cols_t *b = &h->batch;
+	const int same_sv = t->active && t->prn == c->prn;
+	if (!same_sv || t->g0.week != c->g0.week || t->g0.sec != c->g0.sec)
+	{
+		gpusim_nav_frame f;
+		memset(&f, 0, sizeof(f));
+		f.wn = (uint32_t)((unsigned long)(c->g0.week % 1024));   /* gpssim.c:1480 */
+		f.tow = (uint32_t)(((unsigned long)c->g0.sec) / 6UL);     /* gpssim.c:1481 */
+		if (same_sv)
+		{
+			/* refresh, generateNavMsg(grx, &chan[i], 0) (gpssim.c:2300-2304): subframes as they were before
+			 * the refresh; words 0..9 are the previous frame's words 50..59 (gpssim.c:1504-1511) */
+			memcpy(f.sbf, t->seen_sbf, sizeof(f.sbf));
+			memcpy(f.first, t->frame.sbf[4], sizeof(f.first));
+			f.tow_first = t->frame.tow + 5u;
+		}
+		else
+		{
+			/* fresh channel, generateNavMsg(grx, &chan[i], 1) right after eph2sbf (gpssim.c:1604-1608) */
+			nav_copy_sbf(f.sbf, c->sbf);
+			memcpy(f.first, f.sbf[4], sizeof(f.first));
+			f.tow_first = f.tow;
+		}
+		t->frame = f;
+		t->g0 = c->g0;
+		t->prn = c->prn;
+		t->batch_index = -1;
+	}
+	if (t->batch_index < 0)
+	{
+		if (b->n_frames >= b->cap_frames)
+		{
+			b->cap_frames = b->cap_frames ? 2 * b->cap_frames : 64;
+			b->frames = xrealloc(b->frames, (size_t)b->cap_frames * sizeof(gpusim_nav_frame));
+			b->frames_expect = xrealloc(b->frames_expect, (size_t)b->cap_frames * N_DWRD * sizeof(uint32_t));
+		}
+		b->frames[b->n_frames] = t->frame;
+		if (h->nav_check || h->nav_dump != NULL)
+		{
+			uint32_t *x = b->frames_expect + (size_t)b->n_frames * N_DWRD;
+			int k;
+			for (k = 0; k < N_DWRD; k++)
+				x[k] = (uint32_t)c->dwrd[k];
+			if (h->nav_dump != NULL) /* request + what generateNavMsg() made of it: tests/test_navmsg.py */
+			{
+				fwrite(&t->frame, sizeof(t->frame), 1, h->nav_dump);
+				fwrite(x, sizeof(uint32_t), N_DWRD, h->nav_dump);
+			}
+		}
+		t->batch_index = b->n_frames++;
+		h->nav_frames_built++;
+	}
+	t->active = 1;
+	nav_copy_sbf(t->seen_sbf, c->sbf);
+	return t->batch_index;
+}
+
 /* hand the filled batch to the next GPU: swap it into a free ring slot */
 static void queue_batch(gpusim_hook *h)
 {
@@ -660,6 +799,7 @@ static void queue_batch(gpusim_hook *h)
 	s->rows = h->batch;
 	h->batch = tmp;
 	h->batch.n = 0;
+	nav_new_batch(h);
 	s->state = SLOT_QUEUED;
 	h->seq_filled++;
 	pthread_cond_broadcast(&h->cv);
@@ -686,7 +826,10 @@ static void flush_batch(gpusim_hook *h)
 	if (!h->dryrun)
 		queue_batch(h); /* generation and fwrite happen on the worker / writer threads */
 	else
+	{
 		h->batch.n = 0;
+		nav_new_batch(h);
+	}
 }
 
 static int default_host_threads(void)
@@ -719,6 +862,10 @@ gpusim_hook *gpusim_hook_open(int iq_buff_size, double delt, int data_format, FI
 	h->carrier_mode = GPUSIM_CARRIER_INT;
 #endif
 	h->dryrun = ((s = getenv("GPUSIM_DRYRUN")) != NULL && atoi(s) != 0);
+	h->nav_device = ((s = getenv("GPUSIM_NAV_DEVICE")) != NULL && atoi(s) != 0);
+	h->nav_check = h->nav_device && ((s = getenv("GPUSIM_NAV_CHECK")) != NULL && atoi(s) != 0);
+	if (h->nav_device && (s = getenv("GPUSIM_NAV_DUMP")) != NULL && *s && (h->nav_dump = fopen(s, "wb")) == NULL)
+		die("cannot open GPUSIM_NAV_DUMP", s);
 	h->dump_path = getenv("GPUSIM_DUMP");
 
 	h->ndev = 1;
@@ -758,6 +905,7 @@ gpusim_hook *gpusim_hook_open(int iq_buff_size, double delt, int data_format, FI
 	}
 	cols_reserve(&h->batch, batch);
 	h->batch.cap = batch;
+	nav_new_batch(h);
 
 	h->host_threads = default_host_threads();
 	if ((s = getenv("GPUSIM_HOST_THREADS")) != NULL && atoi(s) > 0)
@@ -822,6 +970,8 @@ void gpusim_hook_epoch(gpusim_hook *h, channel_t *chan, const int *gain)
 			b->nav_bits[o] = 0; b->gain[o] = 0; b->carr_phasestep[o] = 0;
 			b->carr_phase[o] = 0; b->f_carr[o] = 0.0; b->carr_phase_f[o] = 0.0;
 			b->iword[o] = 0; b->ibit[o] = 0; b->carr_init[o] = 0.0;
+			b->nav_frame[o] = 0;
+			h->nav[i].active = 0;
 			continue;
 		}
 
@@ -830,6 +980,7 @@ void gpusim_hook_epoch(gpusim_hook *h, channel_t *chan, const int *gain)
 		b->code_phase[o] = chan[i].code_phase;
 		b->icode[o] = chan[i].icode;
 		b->nav_bits[o] = gpusim_pack_nav_bits(chan[i].dwrd, N_DWRD, chan[i].iword, chan[i].ibit);
+		b->nav_frame[o] = h->nav_device ? nav_frame_of(h, i, &chan[i]) : 0;
 		b->gain[o] = gain[i];
 		b->iword[o] = chan[i].iword;
 		b->ibit[o] = chan[i].ibit;
@@ -929,6 +1080,8 @@ void gpusim_hook_close(gpusim_hook *h)
 		        now_s() - h->t_open, h->t_ctx, h->t_ranges, h->t_chains, h->t_wait, h->cap_max);
 	if (h->dump_path != NULL)
 		write_dump(h);
+	if (h->nav_dump != NULL)
+		fclose(h->nav_dump);
 	free(h->ra.rho);
 	cols_free(&h->batch);
 	cols_free(&h->dump);

@@ -347,3 +347,79 @@ double oracle_carrier_phase_checkpoints(double carr_phase, double f_carr, double
 	}
 	return carr_phase;
 }
+
+/*
+ * Navigation data words: what generateNavMsg() (gpssim.c:1467-1547) leaves in
+ * chan->dwrd[60], restated from IS-GPS-200 20.3.5.2 instead of from the reference's mask arithmetic
+ * (computeChecksum, gpssim.c:693-756): every parity bit is the XOR of the listed data bits d1..d24
+ * (Table 20-XIV) and of D29* or D30* of the word before; D30* inverts the data bits; in the words whose
+ * bits 23/24 carry no information (words 2 and 10 of a subframe) those two are chosen so that D29 = D30 = 0.
+ * Pinned against the reference's own generateNavMsg() through oracle/_ref/libgpssim_ref_int.so
+ * (tests/test_navmsg.py).
+ *
+ *   sbf50      the five subframes from eph2sbf() (chan->sbf, gpssim.h:174), 24 source bits in bits 29..6
+ *   first10    source words of dwrd[0..9]: chan->sbf[4] of the call that built the previous frame
+ *              (init = 1: of this call, gpssim.c:1484-1503)
+ *   tow_first  TOW count in their hand-over word; tow: ((unsigned long)g0.sec)/6; wn: g0.week%1024
+ */
+static const signed char nav_parity_taps[6][16] = {
+	{1, 2, 3, 5, 6, 10, 11, 12, 13, 14, 17, 18, 20, 23, 0},          /* D25, with D29* */
+	{2, 3, 4, 6, 7, 11, 12, 13, 14, 15, 18, 19, 21, 24, 0},          /* D26, with D30* */
+	{1, 3, 4, 5, 7, 8, 12, 13, 14, 15, 16, 19, 20, 22, 0},           /* D27, with D29* */
+	{2, 4, 5, 6, 8, 9, 13, 14, 15, 16, 17, 20, 21, 23, 0},           /* D28, with D30* */
+	{1, 3, 5, 6, 7, 9, 10, 14, 15, 16, 17, 18, 21, 22, 24, 0},       /* D29, with D30* */
+	{3, 5, 6, 8, 9, 10, 11, 13, 15, 19, 22, 23, 24, 0},              /* D30, with D29* */
+};
+static const int nav_parity_uses_d29[6] = {1, 0, 1, 0, 0, 1};
+
+static int nav_parity_bit(int row, const int *d /* d[1..24] */, int d29s, int d30s)
+{
+	int p = nav_parity_uses_d29[row] ? d29s : d30s, k;
+	for (k = 0; nav_parity_taps[row][k]; k++)
+		p ^= d[(int)nav_parity_taps[row][k]];
+	return p;
+}
+
+static uint32_t nav_transmitted_word(uint32_t source24 /* d1 in bit 23 */, int d29s, int d30s, int free_tail)
+{
+	int d[25], k;
+	uint32_t w = 0;
+	for (k = 1; k <= 24; k++)
+		d[k] = (int)((source24 >> (24 - k)) & 1u);
+	if (free_tail)
+	{
+		/* d24 enters D29 and D30, d23 only D30: settle D29 with d24, then D30 with d23 */
+		if (nav_parity_bit(4, d, d29s, d30s))
+			d[24] ^= 1;
+		if (nav_parity_bit(5, d, d29s, d30s))
+			d[23] ^= 1;
+	}
+	for (k = 1; k <= 24; k++)
+		w = (w << 1) | (uint32_t)(d[k] ^ d30s);
+	for (k = 0; k < 6; k++)
+		w = (w << 1) | (uint32_t)nav_parity_bit(k, d, d29s, d30s);
+	return w;
+}
+
+void oracle_nav_frame(const uint32_t *sbf50, const uint32_t *first10, uint32_t tow_first, uint32_t tow, uint32_t wn,
+                      uint32_t *dwrd60)
+{
+	int sub, i;
+	uint32_t before = 0; /* the reference starts a frame from prevwrd = 0 or from a word ending in two zero bits */
+	for (sub = 0; sub < 6; sub++)
+	{
+		const uint32_t *src = sub == 0 ? first10 : sbf50 + 10 * (sub - 1);
+		const uint32_t count = sub == 0 ? tow_first : tow + (uint32_t)sub;
+		for (i = 0; i < 10; i++)
+		{
+			uint32_t s = src[i];
+			if (sub == 1 && i == 2)
+				s |= (wn & 0x3ffu) << 20;
+			if (i == 1)
+				s |= (count & 0x1ffffu) << 13;
+			before = nav_transmitted_word((s >> 6) & 0xffffffu, (int)(((before >> 1) | (s >> 31)) & 1u),
+			                              (int)((before | (s >> 30)) & 1u), i == 1 || i == 9);
+			dwrd60[10 * sub + i] = before;
+		}
+	}
+}

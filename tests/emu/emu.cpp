@@ -486,4 +486,18 @@ double emu_phase_chain_tab(double x0, double d, double M, int n_end, int every, 
     return d < 0.0 ? phase_chain_tab<-1>(x0, d, M, n_end, every, tab, emit) : phase_chain_tab<1>(x0, d, M, n_end, every, tab, emit);
 }
 
+// K0 on the host: the 60 data words of n frames (k0_navmsg) and the 32 data bits of a row (k0_navbits)
+void emu_nav_build(const gpusim_nav_frame *frames, int n, uint32_t *dwrd)
+{
+    static_assert(sizeof(gpusim_nav_frame) == sizeof(NavFrame), "layout");
+    for (int f = 0; f < n; f++) {
+        NavFrame nf;
+        memcpy(&nf, &frames[f], sizeof(nf));
+        for (int sub = 0; sub < kNavSubframes; sub++)
+            nav_build_subframe(nf, sub, dwrd + (size_t)f * kNavWords);
+    }
+}
+uint32_t emu_nav_row_bits(const uint32_t *dwrd60, int iword, int ibit) { return nav_row_bits(dwrd60, iword, ibit); }
+uint32_t emu_nav_word(uint32_t src, int solve_tail) { return nav_word(src, solve_tail != 0); }
+
 } // extern "C"

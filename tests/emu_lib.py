@@ -49,6 +49,10 @@ def lib() -> ctypes.CDLL:
         _lib.emu_fast_runs.restype = ctypes.c_long
         _lib.emu_phase_chain_tab.restype = ctypes.c_double
         _lib.emu_phase_chain_tab.argtypes = _lib.emu_phase_chain.argtypes
+        _lib.emu_nav_build.restype = None
+        _lib.emu_nav_build.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        _lib.emu_nav_row_bits.restype = ctypes.c_uint32
+        _lib.emu_nav_row_bits.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     return _lib
 
 
@@ -106,3 +110,17 @@ def phase_chain(x0: float, d: float, modulus: float, n_end: int, every: int):
         assert np.array_equal(x.view(np.uint64), xt.view(np.uint64)) and np.array_equal(w, wt)
         assert np.float64(end).view(np.uint64) == np.float64(end_t).view(np.uint64)
     return x, w, end
+
+
+def nav_build(frames: np.ndarray) -> np.ndarray:
+    """k0_navmsg on the CPU: the 60 data words of every frame (NAV_FRAME array)."""
+    from gps_sdr_sim_b200.table import NAV_FRAME
+    f = np.ascontiguousarray(frames, dtype=NAV_FRAME)
+    out = np.zeros((f.size, 60), dtype=np.uint32)
+    lib().emu_nav_build(f.ctypes.data, f.size, out.ctypes.data)
+    return out
+
+
+def nav_row_bits(dwrd60: np.ndarray, iword: int, ibit: int) -> int:
+    a = np.ascontiguousarray(dwrd60, dtype=np.uint32)
+    return int(lib().emu_nav_row_bits(a.ctypes.data, iword, ibit))

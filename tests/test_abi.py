@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     lib = gs.load_library()
     for name in declared_functions():
         assert hasattr(lib, name), f"{name} not exported by libgpusim.so"
-    assert lib.gpusim_abi_version() == 1
+    assert lib.gpusim_abi_version() == 2
     assert lib.gpusim_strerror(0) == b"ok"
 
 
@@ -35,14 +35,16 @@ def test_library_is_the_in_tree_cuda_build():
     assert os.path.dirname(path) == os.path.join(ROOT, "gps_sdr_sim_b200")
     # the sm_100a cubin is embedded in the shared object
     blob = open(path, "rb").read()
-    assert b"sm_100a" in blob and b"k2_synth" in blob and b"k1_chain" in blob
+    assert b"sm_100a" in blob and b"k2_synth" in blob and b"k1_chain" in blob and b"k0_navmsg" in blob
 
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(api._Config) == 32
     assert ctypes.sizeof(api.Timing) == 24
     from gps_sdr_sim_b200.table import CEpochTable
-    assert ctypes.sizeof(CEpochTable) == 8 + 10 * 8
+    assert ctypes.sizeof(CEpochTable) == 8 + 13 * 8
+    from gps_sdr_sim_b200.table import NAV_FRAME
+    assert NAV_FRAME.itemsize == 256 and NAV_FRAME.fields["first"][1] == 200 and NAV_FRAME.fields["tow"][1] == 244
 
 
 def test_bad_config_rejected_before_touching_cuda():

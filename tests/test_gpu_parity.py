@@ -22,7 +22,7 @@ def digests(buf, table):
 @pytest.fixture(scope="module", autouse=True)
 def _gpu(gpu_required):
     lib = gs.load_library(build_if_missing=False)   # the prebuilt in-tree sm_100a library
-    assert lib.gpusim_abi_version() == 1
+    assert lib.gpusim_abi_version() == 2
 
 
 @pytest.mark.parametrize("name", ALL_GOLDEN)

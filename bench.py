@@ -287,7 +287,46 @@ def other_configs(gs, torch, device):
                      "samples_per_s": samples / ((k1 + k2) / 1e3), "x_realtime": samples / ((k1 + k2) / 1e3) / fs,
                      "k2_gsample_channels_per_s": float((t.cols["prn"] > 0).sum()) * t.samples_per_epoch / (k2 / 1e3) / 1e9,
                      "k2_output_gb_per_s": t.n_epochs * t.epoch_bytes / 1e9 / (k2 / 1e3)}
+    res["k0_nav_build"] = nav_build_check(gs, device)
     return res
+
+
+def nav_build_check(gs, device, n_frames: int = 4096):
+    """wall clock of one gpusim_nav_build call (H2D of the requests + k0_navmsg + sync) for a day's worth of
+    frames of one satellite pair, and its words against the oracle (outside any timed region)"""
+    import ctypes
+    import numpy as np
+    rng = np.random.default_rng(11)
+    f = np.zeros(n_frames, dtype=gs.NAV_FRAME)
+    f["sbf"] = (rng.integers(0, 1 << 24, (n_frames, 5, 10), dtype=np.uint64) << np.uint64(6)).astype(np.uint32)
+    f["first"] = f["sbf"][:, 4]
+    f["tow"] = f["tow_first"] = rng.integers(0, 100800, n_frames)
+    f["wn"] = 799
+    with gs.GpuSim(N_SAMPLES, 1.0 / (10.0 * N_SAMPLES), FMT, 0, max_batch_epochs=1, device=device) as sim:
+        best = None
+        for _ in range(4):
+            t0 = time.perf_counter()
+            sim.nav_build(f)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        words = sim.nav_read(0, 64)
+    ok = None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib
+        olib = oracle_lib.lib()
+        olib.oracle_nav_frame.restype = None
+        olib.oracle_nav_frame.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p]
+        ok = True
+        for fr, w in zip(f[:64], words):
+            want = np.zeros(60, dtype=np.uint32)
+            a, b = np.ascontiguousarray(fr["sbf"]), np.ascontiguousarray(fr["first"])
+            olib.oracle_nav_frame(a.ctypes.data, b.ctypes.data, int(fr["tow_first"]), int(fr["tow"]), int(fr["wn"]), want.ctypes.data)
+            ok = ok and bool(np.array_equal(w, want))
+    except Exception:  # noqa: BLE001 - the checker is optional equipment
+        pass
+    return {"what": "gpusim_nav_build: generateNavMsg + computeChecksum (gpssim.c:1467-1547, :693-756) on the device",
+            "frames": n_frames, "words": 60 * n_frames, "call_ms": round(best * 1e3, 4), "words_match_oracle": ok}
 
 
 def ncu_live(table_path: str, timeout_s: int = 240):

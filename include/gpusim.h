@@ -4,8 +4,9 @@
  * This is the drop-in boundary for ONE path of gps-sdr-sim: the per-sample IQ
  * synthesis loop and output quantise/pack of the reference
  * (gpssim.c:2190-2264 and gpssim.c:2266-2288).  Everything above it - RINEX
- * parsing, orbit propagation, computeRange/computeCodePhase, generateNavMsg,
- * allocateChannel, the CLI - stays the reference's own host C code.  The host
+ * parsing, orbit propagation, computeRange/computeCodePhase, eph2sbf,
+ * allocateChannel, the CLI - stays the reference's own host C code
+ * (generateNavMsg too, unless the host opts for gpusim_nav_build below).  The host
  * records, for every 0.1 s epoch and channel slot, the state the reference's
  * sample loop would have started from (one row of gpusim_epoch_table) and
  * hands batches of epochs to gpusim_generate_epochs*(), which returns exactly

@@ -2,7 +2,8 @@
 """Randomised parity sweep: the CUDA path through the C ABI against the oracle on seeded random tables
 that leave the envelopes of the reference's scenarios (epoch lengths from 104 samples to 20 MS/s, 1..16
 channels, ragged slots, extreme Doppler and code rates, gains in and outside the tuned range, every
-output format, both carrier modes, every kernel option, back-to-back device calls).
+output format, both carrier modes, every kernel option, back-to-back device calls, rows that take their data
+bits from device-built navigation frames).
 
 usage: python tools/fuzz_parity.py [cases] [seed]      (B200 box; exits 1 on the first mismatch)
 """
@@ -76,6 +77,38 @@ def random_table():
     return t, opts, note
 
 
+def by_reference(t):
+    """the same rows taking their data bits from device-built navigation frames.  Returns (table for the
+    oracle: 32 data bits per row cut from the oracle's words, table for the GPU: frame / iword / ibit per row, frames)."""
+    import ctypes
+    n = int(rng.integers(1, 40))
+    frames = np.zeros(n, dtype=gs.NAV_FRAME)
+    frames["sbf"] = (rng.integers(0, 1 << 24, (n, 5, 10), dtype=np.uint64) << np.uint64(6)).astype(np.uint32)
+    frames["first"] = (rng.integers(0, 1 << 24, (n, 10), dtype=np.uint64) << np.uint64(6)).astype(np.uint32)
+    frames["tow"] = rng.integers(0, 100800, n)
+    frames["tow_first"] = rng.integers(0, 100800, n)
+    frames["wn"] = rng.integers(0, 1024, n)
+    olib = oracle_lib.lib()
+    olib.oracle_nav_frame.restype = None
+    olib.oracle_nav_frame.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p]
+    words = np.zeros((n, 60), dtype=np.uint32)
+    for i, f in enumerate(frames):
+        a, b = np.ascontiguousarray(f["sbf"]), np.ascontiguousarray(f["first"])
+        olib.oracle_nav_frame(a.ctypes.data, b.ctypes.data, int(f["tow_first"]), int(f["tow"]), int(f["wn"]), words[i].ctypes.data)
+    shape = t.cols["prn"].shape
+    nav_frame = rng.integers(0, n, shape).astype(np.int32)
+    iword = rng.integers(0, 60, shape).astype(np.int32)
+    ibit = rng.integers(0, 30, shape).astype(np.int32)
+    bits = np.zeros(shape, dtype=np.uint32)
+    for e in range(shape[0]):
+        for k in range(shape[1]):
+            bits[e, k] = gs.pack_nav_bits(words[nav_frame[e, k]].astype(np.uint64), int(iword[e, k]), int(ibit[e, k]))
+    t_oracle = gs.EpochTable(t.samples_per_epoch, t.delt, t.data_format, t.carrier_mode, dict(t.cols, nav_bits=bits))
+    t_gpu = gs.EpochTable(t.samples_per_epoch, t.delt, t.data_format, t.carrier_mode,
+                          dict(t.cols, nav_frame=nav_frame, iword=iword, ibit=ibit), nav_by_reference=True)
+    return t_oracle, t_gpu, frames
+
+
 GUARD = 4096          # poisoned bytes either side of the caller's device output buffer
 POISON = 0xA5
 
@@ -91,11 +124,19 @@ def sweep(cases, seed, verbose=True):
     stream = torch.cuda.Stream()
     for case in range(cases):
         t, opts, note = random_table()
-        want = oracle_lib.generate(t)
+        frames = None
+        if rng.random() < 0.2:      # rows by reference into device-built navigation frames
+            t_oracle, t, frames = by_reference(t)
+            note += " +navref"
+            want = oracle_lib.generate(t_oracle)
+        else:
+            want = oracle_lib.generate(t)
         eb = t.epoch_bytes
         with gs.GpuSim.for_table(t) as sim:
             for k, v in opts.items():
                 sim.set_option(k, v)
+            if frames is not None:
+                sim.nav_build(frames)
             how = int(rng.integers(3))
             if how == 0:
                 got = sim.generate_epochs(t)

@@ -873,7 +873,7 @@ cudaError_t launch_synth(const DeviceJob &job, SynthKernel which, cudaStream_t s
     if (job.n_epochs == 0)
         return cudaSuccess;
 #ifdef GS_ONLY_LEAN8 // development builds (SASS inspection): one instantiation, compiles in seconds
-    return launch_lean<8, 32>(job, stream);
+    return launch_lean<8, GS_LEAN_S>(job, stream);
 #else
 #define GS_DISPATCH(FMTV)                                                        \
     if (which == SynthKernel::Tuned32) return launch_tuned<FMTV, 32>(job, stream); \

@@ -269,6 +269,23 @@ __device__ __forceinline__ void sts_u32x2(uint32_t a, uint32_t v0, uint32_t v1)
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v0), "r"(v1));
 }
 
+__device__ __forceinline__ uint4 ldg_u32x4(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+// The row of the next channel through an explicit ld.global: with a plain C++ load ptxas re-derived the shared-window
+// base (S2UR + UMOV + ULEA) in every trip of the channel loop and spilled 28 bytes; with this form it does neither.
+#ifndef GS_LEAN_ASM_ROW
+#define GS_LEAN_ASM_ROW 1
+#endif
+#if GS_LEAN_ASM_ROW
+#define GS_LEAN_ROW_LOAD(p) ldg_u32x4(p)
+#else
+#define GS_LEAN_ROW_LOAD(p) (*(p))
+#endif
+
 // chip_window() through a 32-bit shared-window address: two LDS and one funnel shift
 __device__ __forceinline__ uint32_t chip_window_s(uint32_t negw_s, uint32_t prn, int c0)
 {
@@ -301,7 +318,7 @@ __device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows
     uint4 r0n = make_uint4(0, 0, 0, 0); // d, steps, cthr | prn<<10 | woff<<16
     double xn = 0.0, dcn = 0.0; // (dcn: double carrier only - its load is a trip to L2 like the row's)
     if (live && nc > 0) {
-        r0n = rows4[0];
+        r0n = CF ? rows4[0] : GS_LEAN_ROW_LOAD(rows4); // (double carrier: the explicit ld.global measures 0.6 % slower, 5.421 -> 5.454 ms)
         xn = lds_f64(sa);
         if (CF)
             dcn = dcs[0];
@@ -313,7 +330,7 @@ __device__ __forceinline__ void synth_run(const K2Smem<A> &sm, const uint4 *rows
         const double x = xn;
         const double dc = dcn;
         if (live && k + 1 < nc) {
-            r0n = rows4[2 * k + 2];
+            r0n = CF ? rows4[2 * k + 2] : GS_LEAN_ROW_LOAD(rows4 + 2 * k + 2);
             xn = lds_f64(sa + G::kStride);
             if (CF)
                 dcn = dcs[k + 1];
@@ -549,22 +566,6 @@ __device__ __forceinline__ void sts_u32x4(uint32_t a, uint32_t v0, uint32_t v1, 
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v0), "r"(v1), "r"(v2), "r"(v3));
 }
 
-__device__ __forceinline__ uint4 ldg_u32x4(const uint4 *p)
-{
-    uint4 v;
-    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
-}
-// The row of the next channel through an explicit ld.global: with a plain C++ load ptxas re-derived the shared-window
-// base (S2UR + UMOV + ULEA) in every trip of the channel loop and spilled 28 bytes; with this form it does neither.
-#ifndef GS_LEAN_ASM_ROW
-#define GS_LEAN_ASM_ROW 1
-#endif
-#if GS_LEAN_ASM_ROW
-#define GS_LEAN_ROW_LOAD(p) ldg_u32x4(p)
-#else
-#define GS_LEAN_ROW_LOAD(p) (*(p))
-#endif
 
 struct LeanSmem {
     const uint64_t *lut; // replicated carrier table (float2 entries)

@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 from . import build as _build
-from .table import NAV_FRAME, CEpochTable, EpochTable, epoch_bytes
+from .table import NAV_EPH, NAV_FRAME, NAV_FRAME_REF, NAV_IONO, CEpochTable, EpochTable, epoch_bytes
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # GPUSIM_LIB: load another build of the same library (kernel experiments); default = the in-tree build
@@ -48,7 +48,7 @@ EXPORTS = (
     "gpusim_upload_table", "gpusim_generate_device", "gpusim_get_timing", "gpusim_set_option",
     "gpusim_carrier_lut", "gpusim_ca_code", "gpusim_pack_nav_bits", "gpusim_advance_carrier_f64",
     "gpusim_host_alloc", "gpusim_host_free", "gpusim_debug_guard_violations",
-    "gpusim_nav_build", "gpusim_nav_read",
+    "gpusim_nav_build", "gpusim_nav_read", "gpusim_nav_build_eph", "gpusim_nav_read_sbf",
 )
 
 
@@ -106,6 +106,10 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.gpusim_nav_build.argtypes = [vp, vp, i32]
     lib.gpusim_nav_read.restype = ctypes.c_int
     lib.gpusim_nav_read.argtypes = [vp, i32, i32, vp]
+    lib.gpusim_nav_build_eph.restype = ctypes.c_int
+    lib.gpusim_nav_build_eph.argtypes = [vp, vp, i32, vp, vp, i32]
+    lib.gpusim_nav_read_sbf.restype = ctypes.c_int
+    lib.gpusim_nav_read_sbf.argtypes = [vp, i32, i32, vp]
     lib.gpusim_advance_carrier_f64.restype = ctypes.c_double
     lib.gpusim_advance_carrier_f64.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_double, i32]
     _lib = lib
@@ -231,6 +235,20 @@ class GpuSim:
         """gpusim_nav_build: frames is a NAV_FRAME array, one element per generateNavMsg() call (gpssim.c:1467-1547)."""
         f = np.ascontiguousarray(frames, dtype=NAV_FRAME)
         self._check(self._lib.gpusim_nav_build(self._ctx, f.ctypes.data, f.size))
+
+    def nav_build_eph(self, eph: np.ndarray, iono: np.ndarray, frames: np.ndarray) -> None:
+        """gpusim_nav_build_eph: eph2sbf() (gpssim.c:490-665) on the device too - eph is a NAV_EPH array, iono one NAV_IONO,
+        frames a NAV_FRAME_REF array naming their subframes by index into eph."""
+        e = np.ascontiguousarray(eph, dtype=NAV_EPH)
+        io = np.ascontiguousarray(iono, dtype=NAV_IONO).reshape(1)
+        f = np.ascontiguousarray(frames, dtype=NAV_FRAME_REF)
+        self._check(self._lib.gpusim_nav_build_eph(self._ctx, e.ctypes.data, e.size, io.ctypes.data, f.ctypes.data, f.size))
+
+    def nav_read_sbf(self, first_eph: int, n_eph: int) -> np.ndarray:
+        """The 5 x 10 source words (chan->sbf) the device made of ephemerides [first_eph, first_eph + n_eph)."""
+        out = np.empty((n_eph, 5, 10), dtype=np.uint32)
+        self._check(self._lib.gpusim_nav_read_sbf(self._ctx, first_eph, n_eph, out.ctypes.data))
+        return out
 
     def nav_read(self, first_frame: int, n_frames: int) -> np.ndarray:
         """The 60 data words (chan->dwrd) of frames [first_frame, first_frame + n_frames), as built on the device."""

@@ -72,6 +72,9 @@ struct gpusim_ctx {
     NavFrame *d_nav_req = nullptr;
     uint32_t *d_nav_words = nullptr;
     int nav_capacity = 0, nav_frames = 0;
+    NavEph *d_nav_eph = nullptr;    // gpusim_nav_build_eph: ephemerides and the 50 subframe words k0_eph2sbf makes of each
+    uint32_t *d_nav_sbf = nullptr;
+    int nav_eph_capacity = 0, nav_ephs = 0;
 
     // output
     uint8_t *d_out = nullptr; // lazily: max_batch_epochs * epoch_bytes
@@ -688,13 +691,78 @@ int gpusim_nav_build(gpusim_ctx *ctx, const gpusim_nav_frame *frames, int32_t n_
         GS_CUDA(ctx, dev_alloc(ctx, &ctx->d_nav_words, (size_t)cap * kNavWords * sizeof(uint32_t)));
         ctx->nav_capacity = cap;
     }
-    ctx->nav_frames = 0;
+    ctx->nav_frames = ctx->nav_ephs = 0;
     if (n_frames > 0) {
         GS_CUDA(ctx, cudaMemcpyAsync(ctx->d_nav_req, frames, (size_t)n_frames * sizeof(NavFrame), cudaMemcpyHostToDevice, ctx->s_compute));
         GS_CUDA(ctx, launch_navmsg(ctx->d_nav_req, n_frames, ctx->d_nav_words, ctx->s_compute));
         GS_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute)); // `frames` is the caller's again
     }
     ctx->nav_frames = n_frames;
+    return GPUSIM_OK;
+}
+
+int gpusim_nav_build_eph(gpusim_ctx *ctx, const gpusim_nav_eph *eph, int32_t n_eph, const gpusim_nav_iono *iono,
+                         const gpusim_nav_frame_ref *frames, int32_t n_frames)
+{
+    static_assert(sizeof(gpusim_nav_eph) == sizeof(NavEph) && sizeof(gpusim_nav_iono) == sizeof(NavIono) &&
+                      sizeof(gpusim_nav_frame_ref) == sizeof(NavFrameRef) && sizeof(NavFrameRef) <= sizeof(NavFrame),
+                  "ABI structs are the device layouts");
+    if (!ctx || n_eph < 0 || n_frames < 0 || (n_eph > 0 && !eph) || (n_frames > 0 && !frames) || !iono)
+        return GPUSIM_ERR_ARG;
+    if ((uint32_t)n_frames > kNavRefMaxFrames)
+        return fail(ctx, GPUSIM_ERR_CAPACITY, "%d navigation frames, at most %u per call", n_frames, kNavRefMaxFrames);
+    for (int f = 0; f < n_frames; f++)
+        if (frames[f].eph < 0 || frames[f].eph >= n_eph || frames[f].eph_first < 0 || frames[f].eph_first >= n_eph)
+            return fail(ctx, GPUSIM_ERR_ARG, "frame %d names ephemerides %d / %d, have %d", f, frames[f].eph, frames[f].eph_first, n_eph);
+    GS_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    {
+        const int rc_drain = drain(ctx);
+        if (rc_drain != GPUSIM_OK)
+            return rc_drain;
+    }
+    if (n_frames > ctx->nav_capacity) {
+        const int cap = std::max(n_frames, std::max(64, 2 * ctx->nav_capacity));
+        GS_CUDA(ctx, dev_alloc(ctx, &ctx->d_nav_req, (size_t)cap * sizeof(NavFrame)));
+        GS_CUDA(ctx, dev_alloc(ctx, &ctx->d_nav_words, (size_t)cap * kNavWords * sizeof(uint32_t)));
+        ctx->nav_capacity = cap;
+    }
+    if (n_eph > ctx->nav_eph_capacity) {
+        const int cap = std::max(n_eph, std::max(64, 2 * ctx->nav_eph_capacity));
+        GS_CUDA(ctx, dev_alloc(ctx, &ctx->d_nav_eph, (size_t)cap * sizeof(NavEph)));
+        GS_CUDA(ctx, dev_alloc(ctx, &ctx->d_nav_sbf, (size_t)cap * kNavSbfWords * sizeof(uint32_t)));
+        ctx->nav_eph_capacity = cap;
+    }
+    ctx->nav_frames = ctx->nav_ephs = 0;
+    NavIono io;
+    memcpy(&io, iono, sizeof(io));
+    if (n_eph > 0) {
+        GS_CUDA(ctx, cudaMemcpyAsync(ctx->d_nav_eph, eph, (size_t)n_eph * sizeof(NavEph), cudaMemcpyHostToDevice, ctx->s_compute));
+        GS_CUDA(ctx, launch_eph2sbf(ctx->d_nav_eph, n_eph, io, ctx->d_nav_sbf, ctx->s_compute));
+    }
+    if (n_frames > 0) {
+        // the frame requests share the buffer of gpusim_nav_build's (larger) requests
+        NavFrameRef *d_ref = reinterpret_cast<NavFrameRef *>(ctx->d_nav_req);
+        GS_CUDA(ctx, cudaMemcpyAsync(d_ref, frames, (size_t)n_frames * sizeof(NavFrameRef), cudaMemcpyHostToDevice, ctx->s_compute));
+        GS_CUDA(ctx, launch_navmsg_ref(d_ref, n_frames, ctx->d_nav_sbf, ctx->d_nav_words, ctx->s_compute));
+    }
+    GS_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
+    ctx->nav_frames = n_frames;
+    ctx->nav_ephs = n_eph;
+    return GPUSIM_OK;
+}
+
+int gpusim_nav_read_sbf(gpusim_ctx *ctx, int32_t first, int32_t n, uint32_t *sbf)
+{
+    if (!ctx || (n > 0 && !sbf))
+        return GPUSIM_ERR_ARG;
+    if (first < 0 || n < 0 || first > ctx->nav_ephs || n > ctx->nav_ephs - first)
+        return fail(ctx, GPUSIM_ERR_ARG, "ephemerides first=%d n=%d outside the %d built", first, n, ctx->nav_ephs);
+    if (n == 0)
+        return GPUSIM_OK;
+    GS_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    GS_CUDA(ctx, cudaMemcpyAsync(sbf, ctx->d_nav_sbf + (size_t)first * kNavSbfWords, (size_t)n * kNavSbfWords * sizeof(uint32_t),
+                                 cudaMemcpyDeviceToHost, ctx->s_compute));
+    GS_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
     return GPUSIM_OK;
 }
 

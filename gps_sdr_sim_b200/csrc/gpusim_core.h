@@ -1361,5 +1361,124 @@ GS_HD void nav_build_subframe(const NavFrame &f, int s, uint32_t *dwrd60)
         nav_subframe(f.sbf[s - 1], f.tow + (uint32_t)s, s == 1 ? (int)(f.week10 & 0x3FFu) : -1, dwrd60 + s * kNavWordsPerSubframe);
 }
 
+// ---- subframes from an ephemeris (replaces eph2sbf, gpssim.c:490-665) ---------------------------------------
+// The 24 source bits of every word of subframes 1..3 (clock and orbit of the satellite itself), of page 18 of
+// subframe 4 (ionosphere / UTC; page 25 when the host has no such data) and of page 25 of subframe 5, IS-GPS-200
+// 20.3.3.3 - 20.3.3.5, from the broadcast values the host read from the RINEX file.  Every field is the
+// reference's quotient "value / LSB" (its divisors are the decimal constants of gpssim.h:44-55 - written out here
+// with the same digits, they are not exact powers of two - and pi = 3.1415926535898), truncated towards zero by the
+// cast to long (rounded half away from zero for the ionosphere / UTC terms), two's complement, cut to the field width.
+struct NavEph {   // what crosses the ABI as gpusim_nav_eph: the fields of ephem_t that eph2sbf() reads (gpssim.h:101-135)
+    double toe_sec, toc_sec;
+    double deltan, cuc, cus, cic, cis, crc, crs, ecc, sqrta, m0, omg0, inc0, aop, omgdot, idot, af0, af1, af2, tgd;
+    int32_t toe_week, iodc, iode, svhlth, codeL2, reserved;
+};
+static_assert(sizeof(NavEph) == 192, "NavEph layout");
+struct NavIono {  // gpusim_nav_iono: ionoutc_t (gpssim.h:137-146)
+    double alpha0, alpha1, alpha2, alpha3, beta0, beta1, beta2, beta3, A0, A1;
+    int32_t vflg, dtls, tot, wnt;
+};
+static_assert(sizeof(NavIono) == 96, "NavIono layout");
+struct NavFrameRef { // gpusim_nav_frame_ref: a frame whose subframes come from device-built ephemeris subframes
+    int32_t eph, eph_first;
+    uint32_t tow_first, tow, week10, reserved;
+};
+static_assert(sizeof(NavFrameRef) == 24, "NavFrameRef layout");
+constexpr int kNavSbfWords = 5 * kNavWordsPerSubframe;
+
+GS_HD int64_t nav_trunc(double q) { return (int64_t)q; }   // (long)(x): towards zero
+GS_HD int64_t nav_round(double q)                          // (signed long)round(x): half away from zero
+{
+#ifdef __CUDA_ARCH__
+    return (int64_t)round(q);
+#else
+    return (int64_t)__builtin_round(q);
+#endif
+}
+// `width` low bits of a two's complement value, placed with their LSB at bit `at` of the word
+GS_HD uint32_t nav_field(int64_t v, int width, int at) { return (uint32_t)(((uint64_t)v & ((1ull << width) - 1ull)) << at); }
+
+GS_HD void nav_eph_subframes(const NavEph &e, const NavIono &io, uint32_t *sbf /* [5][10] */)
+{
+    const double pi = 3.1415926535898;                      // gpssim.h:60
+    const double m5 = 0.03125, m19 = 1.907348632812500e-6, m29 = 1.862645149230957e-9, m31 = 4.656612873077393e-10,
+                 m33 = 1.164153218269348e-10, m43 = 1.136868377216160e-13, m55 = 2.775557561562891e-17,
+                 m50 = 8.881784197001252e-016, m30 = 9.313225746154785e-010, m27 = 7.450580596923828e-009,
+                 m24 = 5.960464477539063e-008;              // gpssim.h:44-55, digit for digit
+    const int64_t toe = nav_trunc(e.toe_sec / 16.0), toc = nav_trunc(e.toc_sec / 16.0);
+    const int64_t iode = e.iode, iodc = e.iodc;
+    const int64_t deltan = nav_trunc(e.deltan / m43 / pi), omgdot = nav_trunc(e.omgdot / m43 / pi), idot = nav_trunc(e.idot / m43 / pi);
+    const int64_t cuc = nav_trunc(e.cuc / m29), cus = nav_trunc(e.cus / m29), cic = nav_trunc(e.cic / m29), cis = nav_trunc(e.cis / m29);
+    const int64_t crc = nav_trunc(e.crc / m5), crs = nav_trunc(e.crs / m5);
+    const int64_t ecc = nav_trunc(e.ecc / m33), sqrta = nav_trunc(e.sqrta / m19);
+    const int64_t m0 = nav_trunc(e.m0 / m31 / pi), omg0 = nav_trunc(e.omg0 / m31 / pi), inc0 = nav_trunc(e.inc0 / m31 / pi),
+                  aop = nav_trunc(e.aop / m31 / pi);
+    const int64_t af0 = nav_trunc(e.af0 / m31), af1 = nav_trunc(e.af1 / m43), af2 = nav_trunc(e.af2 / m55), tgd = nav_trunc(e.tgd / m31);
+    const uint32_t tlm = 0x8Bu << 22;                       // preamble 10001011 in d1..d8, the rest of the TLM word zero
+    for (int i = 0; i < kNavSbfWords; i++)
+        sbf[i] = 0u;
+    for (int sub = 0; sub < 5; sub++) {
+        sbf[sub * 10 + 0] = tlm;
+        sbf[sub * 10 + 1] = (uint32_t)(sub + 1) << 8;       // subframe ID of the hand-over word; TOW count is added per frame
+    }
+    uint32_t *s1 = sbf, *s2 = sbf + 10, *s3 = sbf + 20, *s4 = sbf + 30, *s5 = sbf + 40;
+    // subframe 1: week number (added per frame) | L2 code | URA 0 | health | IODC msbs ; Tgd ; IODC lsbs | toc ; af2 | af1 ; af0
+    s1[2] = nav_field(e.codeL2, 2, 18) | nav_field(e.svhlth, 6, 8) | nav_field(iodc >> 8, 2, 6);
+    s1[6] = nav_field(tgd, 8, 6);
+    s1[7] = nav_field(iodc, 8, 22) | nav_field(toc, 16, 6);
+    s1[8] = nav_field(af2, 8, 22) | nav_field(af1, 16, 6);
+    s1[9] = nav_field(af0, 22, 8);
+    // subframe 2: IODE | Crs ; delta n | M0 msbs ; M0 lsbs ; Cuc | e msbs ; e lsbs ; Cus | sqrt(A) msbs ; sqrt(A) lsbs ; toe
+    s2[2] = nav_field(iode, 8, 22) | nav_field(crs, 16, 6);
+    s2[3] = nav_field(deltan, 16, 14) | nav_field(m0 >> 24, 8, 6);
+    s2[4] = nav_field(m0, 24, 6);
+    s2[5] = nav_field(cuc, 16, 14) | nav_field(ecc >> 24, 8, 6);
+    s2[6] = nav_field(ecc, 24, 6);
+    s2[7] = nav_field(cus, 16, 14) | nav_field(sqrta >> 24, 8, 6);
+    s2[8] = nav_field(sqrta, 24, 6);
+    s2[9] = nav_field(toe, 16, 14);
+    // subframe 3: Cic | Omega0 msbs ; lsbs ; Cis | i0 msbs ; lsbs ; Crc | omega msbs ; lsbs ; Omega dot ; IODE | IDOT
+    s3[2] = nav_field(cic, 16, 14) | nav_field(omg0 >> 24, 8, 6);
+    s3[3] = nav_field(omg0, 24, 6);
+    s3[4] = nav_field(cis, 16, 14) | nav_field(inc0 >> 24, 8, 6);
+    s3[5] = nav_field(inc0, 24, 6);
+    s3[6] = nav_field(crc, 16, 14) | nav_field(aop >> 24, 8, 6);
+    s3[7] = nav_field(aop, 24, 6);
+    s3[8] = nav_field(omgdot, 24, 6);
+    s3[9] = nav_field(iode, 8, 22) | nav_field(idot, 14, 8);
+    // subframe 4: data ID 1, page 18 (SV ID 56: ionosphere and UTC) when the host has the parameters, else page 25 (SV ID 63)
+    if (io.vflg == 1) {
+        const int64_t a0 = nav_round(io.alpha0 / m30), a1 = nav_round(io.alpha1 / m27), a2 = nav_round(io.alpha2 / m24),
+                      a3 = nav_round(io.alpha3 / m24);
+        const int64_t b0 = nav_round(io.beta0 / 2048.0), b1 = nav_round(io.beta1 / 16384.0), b2 = nav_round(io.beta2 / 65536.0),
+                      b3 = nav_round(io.beta3 / 65536.0);
+        const int64_t A0 = nav_round(io.A0 / m30), A1 = nav_round(io.A1 / m50);
+        const int64_t tot = io.tot / 4096, wnt = io.wnt % 256;
+        const int64_t wnlsf = 1929 % 256, dn = 7, dtlsf = 18; // the reference's fixed leap-second schedule (gpssim.c:585-587)
+        s4[2] = nav_field(1, 2, 28) | nav_field(56, 6, 22) | nav_field(a0, 8, 14) | nav_field(a1, 8, 6);
+        s4[3] = nav_field(a2, 8, 22) | nav_field(a3, 8, 14) | nav_field(b0, 8, 6);
+        s4[4] = nav_field(b1, 8, 22) | nav_field(b2, 8, 14) | nav_field(b3, 8, 6);
+        s4[5] = nav_field(A1, 24, 6);
+        s4[6] = nav_field(A0 >> 8, 24, 6);
+        s4[7] = nav_field(A0, 8, 22) | nav_field(tot, 8, 14) | nav_field(wnt, 8, 6);
+        s4[8] = nav_field(io.dtls, 8, 22) | nav_field(wnlsf, 8, 14) | nav_field(dn, 8, 6);
+        s4[9] = nav_field(dtlsf, 8, 22);
+    } else {
+        s4[2] = nav_field(1, 2, 28) | nav_field(63, 6, 22);
+    }
+    // subframe 5: data ID 1, page 25 (SV ID 51): almanac reference time and week
+    s5[2] = nav_field(1, 2, 28) | nav_field(51, 6, 22) | nav_field(nav_trunc(e.toe_sec / 4096.0), 8, 14) | nav_field(e.toe_week % 256, 8, 6);
+}
+
+// subframe s of a frame whose source words are device-built ephemeris subframes
+GS_HD void nav_build_subframe_ref(const NavFrameRef &f, const uint32_t *sbf_all, int s, uint32_t *dwrd60)
+{
+    if (s == 0)
+        nav_subframe(sbf_all + (size_t)f.eph_first * kNavSbfWords + 4 * kNavWordsPerSubframe, f.tow_first, -1, dwrd60);
+    else
+        nav_subframe(sbf_all + (size_t)f.eph * kNavSbfWords + (s - 1) * kNavWordsPerSubframe, f.tow + (uint32_t)s,
+                     s == 1 ? (int)(f.week10 & 0x3FFu) : -1, dwrd60 + s * kNavWordsPerSubframe);
+}
+
 } // namespace gpusim
 #endif

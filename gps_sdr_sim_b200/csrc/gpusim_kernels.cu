@@ -67,6 +67,41 @@ __global__ void __launch_bounds__(128) k0_navbits(DevRow *rows, int n_rows, cons
     rows[r].flags = (uint16_t)(flags & ~kRowNavRef);
 }
 
+// one thread per ephemeris: the five subframes eph2sbf() makes of it (gpssim.c:490-665)
+__global__ void __launch_bounds__(64) k0_eph2sbf(const NavEph *eph, int n_eph, NavIono iono, uint32_t *sbf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_eph)
+        nav_eph_subframes(eph[i], iono, sbf + (size_t)i * kNavSbfWords);
+}
+
+// k0_navmsg for frames that name their subframes by ephemeris index
+__global__ void __launch_bounds__(128) k0_navmsg_ref(const NavFrameRef *frames, int n_frames, const uint32_t *sbf, uint32_t *dwrd)
+{
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = gid / kNavSubframes;
+    if (f >= n_frames)
+        return;
+    nav_build_subframe_ref(frames[f], sbf, gid - f * kNavSubframes, dwrd + (size_t)f * kNavWords);
+}
+
+cudaError_t launch_eph2sbf(const NavEph *eph, int n_eph, const NavIono &iono, uint32_t *sbf, cudaStream_t stream)
+{
+    if (n_eph <= 0)
+        return cudaSuccess;
+    k0_eph2sbf<<<(n_eph + 63) / 64, 64, 0, stream>>>(eph, n_eph, iono, sbf);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_navmsg_ref(const NavFrameRef *frames, int n_frames, const uint32_t *sbf, uint32_t *dwrd, cudaStream_t stream)
+{
+    if (n_frames <= 0)
+        return cudaSuccess;
+    const int threads = 128, total = n_frames * kNavSubframes;
+    k0_navmsg_ref<<<(total + threads - 1) / threads, threads, 0, stream>>>(frames, n_frames, sbf, dwrd);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_navmsg(const NavFrame *frames, int n_frames, uint32_t *dwrd, cudaStream_t stream)
 {
     if (n_frames <= 0)

@@ -63,6 +63,9 @@ enum class SynthKernel { Tuned32 = 0, Tuned16 = 1, Generic = 2 };
 // K0: data words of n_frames navigation frames (60 each); data bits of the rows that reference them
 cudaError_t launch_navmsg(const NavFrame *frames, int n_frames, uint32_t *dwrd, cudaStream_t stream);
 cudaError_t launch_navbits(DevRow *rows, int n_rows, const uint32_t *dwrd, cudaStream_t stream);
+// K0: the five subframes of n_eph ephemerides (50 words each); frames that name their subframes by ephemeris index
+cudaError_t launch_eph2sbf(const NavEph *eph, int n_eph, const NavIono &iono, uint32_t *sbf, cudaStream_t stream);
+cudaError_t launch_navmsg_ref(const NavFrameRef *frames, int n_frames, const uint32_t *sbf, uint32_t *dwrd, cudaStream_t stream);
 // K1: exact code-phase checkpoints for every (epoch, active channel, chunk)
 cudaError_t launch_chain(const DeviceJob &job, ChainAlgo algo, cudaStream_t stream);
 // K2: samples -> bytes

@@ -30,6 +30,16 @@ _NAV_REF = (("nav_frame", np.int32), ("iword", np.int32), ("ibit", np.int32))
 NAV_FRAME = np.dtype([("sbf", np.uint32, (5, 10)), ("first", np.uint32, (10,)), ("tow_first", np.uint32),
                       ("tow", np.uint32), ("wn", np.uint32), ("reserved", np.uint32)])
 assert NAV_FRAME.itemsize == 256
+# struct gpusim_nav_eph / gpusim_nav_iono / gpusim_nav_frame_ref: what eph2sbf() reads of ephem_t / ionoutc_t (gpssim.h:101-146)
+_EPH_DOUBLES = ("toe_sec", "toc_sec", "deltan", "cuc", "cus", "cic", "cis", "crc", "crs", "ecc", "sqrta", "m0", "omg0", "inc0",
+                "aop", "omgdot", "idot", "af0", "af1", "af2", "tgd")
+NAV_EPH = np.dtype([(n, np.float64) for n in _EPH_DOUBLES] +
+                   [(n, np.int32) for n in ("toe_week", "iodc", "iode", "svhlth", "codeL2", "reserved")])
+NAV_IONO = np.dtype([(n, np.float64) for n in ("alpha0", "alpha1", "alpha2", "alpha3", "beta0", "beta1", "beta2", "beta3", "A0", "A1")] +
+                    [(n, np.int32) for n in ("vflg", "dtls", "tot", "wnt")])
+NAV_FRAME_REF = np.dtype([("eph", np.int32), ("eph_first", np.int32), ("tow_first", np.uint32), ("tow", np.uint32),
+                          ("wn", np.uint32), ("reserved", np.uint32)])
+assert NAV_EPH.itemsize == 192 and NAV_IONO.itemsize == 96 and NAV_FRAME_REF.itemsize == 24
 
 
 class CEpochTable(ctypes.Structure):

@@ -213,6 +213,31 @@ int gpusim_get_timing(const gpusim_ctx *ctx, gpusim_timing *out);
 int gpusim_nav_build(gpusim_ctx *ctx, const gpusim_nav_frame *frames, int32_t n_frames);
 int gpusim_nav_read(gpusim_ctx *ctx, int32_t first_frame, int32_t n_frames, uint32_t *dwrd);
 
+/*
+ * The same with eph2sbf() (gpssim.c:490-665) on the device as well: the host hands over the broadcast
+ * ephemerides themselves - the fields of ephem_t / ionoutc_t (gpssim.h:101-146) that eph2sbf() reads, as
+ * readRinexNavAll() filled them - and frames name their subframes by ephemeris index:
+ *   eph        index of the ephemeris whose subframes chan->sbf held when generateNavMsg() ran
+ *   eph_first  index of the ephemeris behind the frame's first ten words (see gpusim_nav_frame.first)
+ * gpusim_nav_read_sbf() copies the 50 source words (chan->sbf) of ephemerides [first, first+n) back.
+ */
+typedef struct gpusim_nav_eph {
+    double toe_sec, toc_sec; /* eph.toe.sec, eph.toc.sec */
+    double deltan, cuc, cus, cic, cis, crc, crs, ecc, sqrta, m0, omg0, inc0, aop, omgdot, idot, af0, af1, af2, tgd;
+    int32_t toe_week, iodc, iode, svhlth, codeL2, reserved;
+} gpusim_nav_eph;
+typedef struct gpusim_nav_iono {
+    double alpha0, alpha1, alpha2, alpha3, beta0, beta1, beta2, beta3, A0, A1;
+    int32_t vflg, dtls, tot, wnt;
+} gpusim_nav_iono;
+typedef struct gpusim_nav_frame_ref {
+    int32_t eph, eph_first;
+    uint32_t tow_first, tow, wn, reserved;
+} gpusim_nav_frame_ref;
+int gpusim_nav_build_eph(gpusim_ctx *ctx, const gpusim_nav_eph *eph, int32_t n_eph, const gpusim_nav_iono *iono,
+                         const gpusim_nav_frame_ref *frames, int32_t n_frames);
+int gpusim_nav_read_sbf(gpusim_ctx *ctx, int32_t first_eph, int32_t n_eph, uint32_t *sbf);
+
 /* Test facility.  A context created with GPUSIM_GUARD=1 in the environment places every device buffer it
  * owns (rows, code-phase checkpoints, work counters, its own output buffer) between two 4 KiB poisoned guard
  * bands.  Returns the number of guard bytes that no longer hold the poison after all work of the context has

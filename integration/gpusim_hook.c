@@ -26,6 +26,9 @@
  *   GPUSIM_NAV_DEVICE    1: navigation data words on the device.  Rows reference frames
  *                        (one per generateNavMsg() call, rebuilt from chan[i].sbf by gpusim_nav_build)
  *                        instead of carrying 32 data bits taken from chan[i].dwrd.
+ *                        2: eph2sbf() on the device as well (gpusim_nav_build_eph): the shim hands over the
+ *                        broadcast ephemerides (the eph[ieph] the epoch loop works with, seen through
+ *                        GPUSIM_HOOK_RANGE) and frames name their subframes by ephemeris index.
  *   GPUSIM_NAV_CHECK     1 (with GPUSIM_NAV_DEVICE): read the device-built words back after every
  *                        build and compare them with the host's chan[i].dwrd; a difference is fatal
  *   GPUSIM_NAV_DUMP      path (with GPUSIM_NAV_DEVICE): every frame request (struct gpusim_nav_frame)
@@ -85,6 +88,12 @@ typedef struct
 	gpusim_nav_frame *frames;
 	uint32_t *frames_expect; /* GPUSIM_NAV_CHECK: chan[i].dwrd[60] as the host built it, per frame */
 	int n_frames, cap_frames;
+	/* GPUSIM_NAV_DEVICE=2: the ephemerides the frames' subframes come from (index = frame_refs[].eph / .eph_first) */
+	gpusim_nav_frame_ref *frame_refs; /* parallel to frames[] */
+	gpusim_nav_eph *ephs;
+	const ephem_t **eph_keys;         /* the host's ephemeris each entry was made from (dedupe) */
+	int n_ephs, cap_ephs;
+	gpusim_nav_iono iono;
 } cols_t;
 
 /* GPUSIM_NAV_DEVICE: what the shim remembers about the frame a channel slot is transmitting */
@@ -98,6 +107,9 @@ typedef struct
 	                                     subframes of a new ephemeris set AFTER that call (gpssim.c:2300-2330) */
 	gpusim_nav_frame frame;  /* the current frame's request */
 	int batch_index;         /* its index in the current batch's frame list, -1 = not registered yet */
+	/* GPUSIM_NAV_DEVICE=2: the host ephemeris behind seen_sbf, behind the current frame's subframes and behind its
+	 * first ten words (eph[ieph][prn-1] of the epoch loop; the arrays live in main() for the whole run) */
+	const ephem_t *seen_eph, *frame_eph, *first_eph;
 } nav_slot_t;
 
 /* the reference's own functions (gpssim.c:789, :1253; external linkage, not declared in gpssim.h) */
@@ -198,7 +210,9 @@ struct gpusim_hook
 	long epochs_written; /* epochs delivered to the output file so far (what a failure report states) */
 	gpusim_config cfg;   /* what every worker creates its context with */
 	size_t epoch_bytes;  /* gpssim.c:2276/:2283/:2287 */
-	int nav_device, nav_check; /* GPUSIM_NAV_DEVICE, GPUSIM_NAV_CHECK */
+	int nav_device, nav_check; /* GPUSIM_NAV_DEVICE (1: subframes from the host, 2: ephemerides from the host), GPUSIM_NAV_CHECK */
+	const ephem_t *cur_eph_set; /* eph[ieph] and ionoutc of the epoch being recorded (from GPUSIM_HOOK_RANGE) */
+	const ionoutc_t *cur_iono;
 	FILE *nav_dump;            /* GPUSIM_NAV_DUMP */
 	nav_slot_t nav[MAX_CHAN];
 	long nav_frames_built;
@@ -264,7 +278,7 @@ static void cols_free(cols_t *c)
 	free(c->prn); free(c->f_code); free(c->code_phase); free(c->icode);
 	free(c->nav_bits); free(c->gain); free(c->carr_phasestep); free(c->carr_phase);
 	free(c->f_carr); free(c->carr_phase_f); free(c->iword); free(c->ibit); free(c->carr_init);
-	free(c->nav_frame); free(c->frames); free(c->frames_expect);
+	free(c->nav_frame); free(c->frames); free(c->frames_expect); free(c->frame_refs); free(c->ephs); free(c->eph_keys);
 	memset(c, 0, sizeof(*c));
 }
 
@@ -501,6 +515,8 @@ void gpusim_hook_range(gpusim_hook *h, range_t *rho, int slot, int iumd, int num
 {
 	lookahead_t *ra = &h->ra;
 	int attempt;
+	h->cur_eph_set = eph_set;
+	h->cur_iono = ionoutc;
 	for (attempt = 0; ra->enabled && attempt < 2; attempt++)
 	{
 		int k = iumd - ra->first;
@@ -627,7 +643,9 @@ static void *worker_main(void *arg)
 		if (h->nav_device)
 		{
 			/* generateNavMsg + computeChecksum for the frames of this batch, on this worker's GPU */
-			rc = gpusim_nav_build(w->ctx, s->rows.frames, s->rows.n_frames);
+			rc = h->nav_device == 2
+			         ? gpusim_nav_build_eph(w->ctx, s->rows.ephs, s->rows.n_ephs, &s->rows.iono, s->rows.frame_refs, s->rows.n_frames)
+			         : gpusim_nav_build(w->ctx, s->rows.frames, s->rows.n_frames);
 			if (rc == GPUSIM_OK && h->nav_check)
 			{
 				uint32_t *got = malloc((size_t)(s->rows.n_frames > 0 ? s->rows.n_frames : 1) * N_DWRD * sizeof(uint32_t));
@@ -706,6 +724,7 @@ static void nav_new_batch(gpusim_hook *h)
 {
 	int i;
 	h->batch.n_frames = 0;
+	h->batch.n_ephs = 0;
 	for (i = 0; i < MAX_CHAN; i++)
 		h->nav[i].batch_index = -1;
 }
@@ -716,6 +735,44 @@ static void nav_copy_sbf(uint32_t dst[5][N_DWRD_SBF], unsigned long src[5][N_DWR
 	for (a = 0; a < 5; a++)
 		for (b = 0; b < N_DWRD_SBF; b++)
 			dst[a][b] = (uint32_t)src[a][b]; /* generateNavMsg reads them into an `unsigned` (gpssim.c:1473) */
+}
+
+/* what eph2sbf() reads of ionoutc_t (gpssim.c:560-579) */
+static void nav_iono_of(const ionoutc_t *io, gpusim_nav_iono *o)
+{
+	memset(o, 0, sizeof(*o));
+	o->alpha0 = io->alpha0; o->alpha1 = io->alpha1; o->alpha2 = io->alpha2; o->alpha3 = io->alpha3;
+	o->beta0 = io->beta0; o->beta1 = io->beta1; o->beta2 = io->beta2; o->beta3 = io->beta3;
+	o->A0 = io->A0; o->A1 = io->A1;
+	o->vflg = io->vflg; o->dtls = io->dtls; o->tot = io->tot; o->wnt = io->wnt;
+}
+
+/* GPUSIM_NAV_DEVICE=2: index of the host ephemeris `e` in the batch's list (what eph2sbf() reads of it, gpssim.c:490-665) */
+static int nav_eph_index(gpusim_hook *h, const ephem_t *e)
+{
+	cols_t *b = &h->batch;
+	gpusim_nav_eph *o;
+	int k;
+	if (e == NULL)
+		die("GPUSIM_NAV_DEVICE=2 needs the GPUSIM_HOOK_RANGE() edit (it is how the shim sees eph[ieph])", NULL);
+	for (k = 0; k < b->n_ephs; k++)
+		if (b->eph_keys[k] == e)
+			return k;
+	if (b->n_ephs >= b->cap_ephs)
+	{
+		b->cap_ephs = b->cap_ephs ? 2 * b->cap_ephs : 32;
+		b->ephs = xrealloc(b->ephs, (size_t)b->cap_ephs * sizeof(gpusim_nav_eph));
+		b->eph_keys = xrealloc(b->eph_keys, (size_t)b->cap_ephs * sizeof(*b->eph_keys));
+	}
+	o = &b->ephs[b->n_ephs];
+	memset(o, 0, sizeof(*o));
+	o->toe_sec = e->toe.sec; o->toc_sec = e->toc.sec; o->toe_week = e->toe.week;
+	o->deltan = e->deltan; o->cuc = e->cuc; o->cus = e->cus; o->cic = e->cic; o->cis = e->cis; o->crc = e->crc; o->crs = e->crs;
+	o->ecc = e->ecc; o->sqrta = e->sqrta; o->m0 = e->m0; o->omg0 = e->omg0; o->inc0 = e->inc0; o->aop = e->aop;
+	o->omgdot = e->omgdot; o->idot = e->idot; o->af0 = e->af0; o->af1 = e->af1; o->af2 = e->af2; o->tgd = e->tgd;
+	o->iodc = e->iodc; o->iode = e->iode; o->svhlth = e->svhlth; o->codeL2 = e->codeL2;
+	b->eph_keys[b->n_ephs] = e;
+	return b->n_ephs++;
 }
 
 /* Frame index (in the batch being filled) of what slot i transmits in this epoch.  A frame is one
@@ -738,6 +795,8 @@ static int nav_frame_of(gpusim_hook *h, int i, channel_t *c)
 			memcpy(f.sbf, t->seen_sbf, sizeof(f.sbf));
 			memcpy(f.first, t->frame.sbf[4], sizeof(f.first));
 			f.tow_first = t->frame.tow + 5u;
+			t->first_eph = t->frame_eph;
+			t->frame_eph = t->seen_eph;
 		}
 		else
 		{
@@ -745,6 +804,7 @@ static int nav_frame_of(gpusim_hook *h, int i, channel_t *c)
 			nav_copy_sbf(f.sbf, c->sbf);
 			memcpy(f.first, f.sbf[4], sizeof(f.first));
 			f.tow_first = f.tow;
+			t->frame_eph = t->first_eph = h->cur_eph_set != NULL ? &h->cur_eph_set[c->prn - 1] : NULL;
 		}
 		t->frame = f;
 		t->g0 = c->g0;
@@ -757,9 +817,20 @@ static int nav_frame_of(gpusim_hook *h, int i, channel_t *c)
 		{
 			b->cap_frames = b->cap_frames ? 2 * b->cap_frames : 64;
 			b->frames = xrealloc(b->frames, (size_t)b->cap_frames * sizeof(gpusim_nav_frame));
+			b->frame_refs = xrealloc(b->frame_refs, (size_t)b->cap_frames * sizeof(gpusim_nav_frame_ref));
 			b->frames_expect = xrealloc(b->frames_expect, (size_t)b->cap_frames * N_DWRD * sizeof(uint32_t));
 		}
 		b->frames[b->n_frames] = t->frame;
+		if (h->nav_device == 2)
+		{
+			gpusim_nav_frame_ref *r = &b->frame_refs[b->n_frames];
+			memset(r, 0, sizeof(*r));
+			r->eph = nav_eph_index(h, t->frame_eph);
+			r->eph_first = nav_eph_index(h, t->first_eph);
+			r->tow_first = t->frame.tow_first;
+			r->tow = t->frame.tow;
+			r->wn = t->frame.wn;
+		}
 		if (h->nav_check || h->nav_dump != NULL)
 		{
 			uint32_t *x = b->frames_expect + (size_t)b->n_frames * N_DWRD;
@@ -770,6 +841,14 @@ static int nav_frame_of(gpusim_hook *h, int i, channel_t *c)
 			{
 				fwrite(&t->frame, sizeof(t->frame), 1, h->nav_dump);
 				fwrite(x, sizeof(uint32_t), N_DWRD, h->nav_dump);
+				if (h->nav_device == 2) /* + the two ephemerides and the ionosphere / UTC block the frame refers to */
+				{
+					gpusim_nav_iono io;
+					nav_iono_of(h->cur_iono, &io);
+					fwrite(&b->ephs[b->frame_refs[b->n_frames].eph], sizeof(gpusim_nav_eph), 1, h->nav_dump);
+					fwrite(&b->ephs[b->frame_refs[b->n_frames].eph_first], sizeof(gpusim_nav_eph), 1, h->nav_dump);
+					fwrite(&io, sizeof(io), 1, h->nav_dump);
+				}
 			}
 		}
 		t->batch_index = b->n_frames++;
@@ -777,6 +856,7 @@ static int nav_frame_of(gpusim_hook *h, int i, channel_t *c)
 	}
 	t->active = 1;
 	nav_copy_sbf(t->seen_sbf, c->sbf);
+	t->seen_eph = h->cur_eph_set != NULL ? &h->cur_eph_set[c->prn - 1] : NULL;
 	return t->batch_index;
 }
 
@@ -823,6 +903,8 @@ static void flush_batch(gpusim_hook *h)
 			cols_append(&h->dump, &h->batch, e);
 
 	h->epochs_done += h->batch.n;
+	if (h->nav_device == 2 && h->cur_iono != NULL)
+		nav_iono_of(h->cur_iono, &h->batch.iono);
 	if (!h->dryrun)
 		queue_batch(h); /* generation and fwrite happen on the worker / writer threads */
 	else
@@ -862,7 +944,7 @@ gpusim_hook *gpusim_hook_open(int iq_buff_size, double delt, int data_format, FI
 	h->carrier_mode = GPUSIM_CARRIER_INT;
 #endif
 	h->dryrun = ((s = getenv("GPUSIM_DRYRUN")) != NULL && atoi(s) != 0);
-	h->nav_device = ((s = getenv("GPUSIM_NAV_DEVICE")) != NULL && atoi(s) != 0);
+	h->nav_device = (s = getenv("GPUSIM_NAV_DEVICE")) != NULL ? (atoi(s) >= 2 ? 2 : atoi(s) != 0) : 0;
 	h->nav_check = h->nav_device && ((s = getenv("GPUSIM_NAV_CHECK")) != NULL && atoi(s) != 0);
 	if (h->nav_device && (s = getenv("GPUSIM_NAV_DUMP")) != NULL && *s && (h->nav_dump = fopen(s, "wb")) == NULL)
 		die("cannot open GPUSIM_NAV_DUMP", s);

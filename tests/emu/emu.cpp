@@ -500,4 +500,17 @@ void emu_nav_build(const gpusim_nav_frame *frames, int n, uint32_t *dwrd)
 uint32_t emu_nav_row_bits(const uint32_t *dwrd60, int iword, int ibit) { return nav_row_bits(dwrd60, iword, ibit); }
 uint32_t emu_nav_word(uint32_t src, int solve_tail) { return nav_word(src, solve_tail != 0); }
 
+// k0_eph2sbf on the host: the 50 source words of n ephemerides
+void emu_eph2sbf(const gpusim_nav_eph *eph, int n, const gpusim_nav_iono *iono, uint32_t *sbf)
+{
+    static_assert(sizeof(gpusim_nav_eph) == sizeof(NavEph) && sizeof(gpusim_nav_iono) == sizeof(NavIono), "layout");
+    NavIono io;
+    memcpy(&io, iono, sizeof(io));
+    for (int i = 0; i < n; i++) {
+        NavEph e;
+        memcpy(&e, &eph[i], sizeof(e));
+        nav_eph_subframes(e, io, sbf + (size_t)i * kNavSbfWords);
+    }
+}
+
 } // extern "C"

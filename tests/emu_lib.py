@@ -124,3 +124,16 @@ def nav_build(frames: np.ndarray) -> np.ndarray:
 def nav_row_bits(dwrd60: np.ndarray, iword: int, ibit: int) -> int:
     a = np.ascontiguousarray(dwrd60, dtype=np.uint32)
     return int(lib().emu_nav_row_bits(a.ctypes.data, iword, ibit))
+
+
+def eph2sbf(eph: np.ndarray, iono: np.ndarray) -> np.ndarray:
+    """k0_eph2sbf on the CPU: [n, 5, 10] source words from a NAV_EPH array and one NAV_IONO."""
+    from gps_sdr_sim_b200.table import NAV_EPH, NAV_IONO
+    e = np.ascontiguousarray(eph, dtype=NAV_EPH)
+    io = np.ascontiguousarray(iono, dtype=NAV_IONO).reshape(1)
+    out = np.zeros((e.size, 5, 10), dtype=np.uint32)
+    f = lib().emu_eph2sbf
+    f.restype = None
+    f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    f(e.ctypes.data, e.size, io.ctypes.data, out.ctypes.data)
+    return out

@@ -181,17 +181,19 @@ def test_full_length_run_equals_reference(name, gpu_required):
     assert sha_g == sha_r, f"{name}: output differs from the reference ({FULL[name][2]})"
 
 
+@pytest.mark.parametrize("level", ["1", "2"])
 @pytest.mark.parametrize("name", ["config3_satellite_300s", "config2_circle_300s", "config4_asshipped_156s"])
-def test_full_length_run_with_device_built_nav_words_equals_reference(name, gpu_required):
+def test_full_length_run_with_device_built_nav_words_equals_reference(name, level, gpu_required):
     """GPUSIM_NAV_DEVICE=1 - the shim hands the library the subframes (chan[i].sbf) of every
     generateNavMsg() call instead of data bits; TOW counts, week number and parity (gpssim.c:1467-1547, :693-756) are
-    computed on the device and every row takes its bits from there.  GPUSIM_NAV_CHECK=1 also compares the device's
-    words with the host's chan[i].dwrd after every build.  Same bytes as the unmodified reference."""
+    computed on the device and every row takes its bits from there.  GPUSIM_NAV_DEVICE=2: the subframes themselves are
+    made on the device too, from the broadcast ephemerides (eph2sbf, gpssim.c:490-665).  GPUSIM_NAV_CHECK=1 also compares
+    the device's words with the host's chan[i].dwrd after every build.  Same bytes as the unmodified reference."""
     mode = FULL[name][0]
     _, host = shipped(mode)
     rc_r, sha_r, n_r, err_r = _reference_digest(name)
     assert rc_r == 0, err_r
-    env = dict(os.environ, GPUSIM_NAV_DEVICE="1", GPUSIM_NAV_CHECK="1")
+    env = dict(os.environ, GPUSIM_NAV_DEVICE=level, GPUSIM_NAV_CHECK="1")
     rc_g, sha_g, n_g, err_g = _stream_digest([host, *_full_argv(name)], env=env)
     assert rc_g == 0, err_g
     assert n_g == n_r > 0

@@ -96,3 +96,37 @@ def test_rows_by_reference_generate_the_same_bytes(fmt, mode):
                             dict(by_ref.cols, nav_frame=np.full_like(nav_frame, frames.size)), nav_by_reference=True)
         with pytest.raises(gs.GpuSimError):
             sim.generate_epochs(bad)
+
+
+def test_device_subframes_equal_the_reference_eph2sbf():
+    """k0_eph2sbf on every valid ephemeris of the reference's RINEX file against the reference's own eph2sbf()
+    (gpssim.c:490-665, through oracle/_ref/libgpssim_ref_int.so), and frames built from them against the oracle."""
+    import ref_nav
+    lib = ref_nav.ref_lib()
+    if lib is None:
+        pytest.fail("oracle/_ref/libgpssim_ref_int.so was not shipped to this GPU box")
+    ephs, iono = ref_nav.broadcast_ephemerides(lib)
+    want = np.stack([ref_nav.ref_subframes(lib, e, iono) for e in ephs])
+    eph_arr, io = ref_nav.as_nav_eph(ephs), ref_nav.as_nav_iono(iono)
+    rng = np.random.default_rng(8)
+    n = 500
+    refs = np.zeros(n, dtype=gs.NAV_FRAME_REF)
+    refs["eph"] = rng.integers(0, len(ephs), n)
+    refs["eph_first"] = rng.integers(0, len(ephs), n)
+    refs["tow"] = rng.integers(0, 100800, n)
+    refs["tow_first"] = rng.integers(0, 100800, n)
+    refs["wn"] = rng.integers(0, 1024, n)
+    with gs.GpuSim(260000, 1.0 / 2.6e6, 16, 0, max_batch_epochs=4) as sim:
+        sim.nav_build_eph(eph_arr, io, refs)
+        assert np.array_equal(sim.nav_read_sbf(0, len(ephs)), want)
+        got = sim.nav_read(0, n)
+        frames = np.zeros(n, dtype=NAV_FRAME)
+        frames["sbf"] = want[refs["eph"]]
+        frames["first"] = want[refs["eph_first"], 4]
+        for k in ("tow", "tow_first", "wn"):
+            frames[k] = refs[k]
+        assert np.array_equal(got, oracle_words(frames))
+        bad = refs.copy()
+        bad["eph"][3] = len(ephs)
+        with pytest.raises(gs.GpuSimError):
+            sim.nav_build_eph(eph_arr, io, bad)

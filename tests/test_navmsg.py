@@ -185,3 +185,60 @@ def test_host_shim_frames_are_what_the_reference_transmits(name, tmp_path):
     assert all(np.array_equal(oracle_frame(f), w) for f, w in zip(recs["frame"][:200], recs["dwrd"][:200]))
     # (a refresh without an ephemeris switch asks for the same words a first frame would: the two kinds only differ
     # after eph2sbf() replaced the subframes, which test_refresh_sequence_with_an_ephemeris_switch constructs)
+
+
+# ---- eph2sbf (gpssim.c:490-665) -------------------------------------------------------------------------------------
+def test_subframes_of_every_broadcast_ephemeris_match_eph2sbf():
+    """Every valid ephemeris of the reference's RINEX file (as its own readRinexNavAll() parses it), with and without
+    ionosphere / UTC parameters, plus perturbed copies that reach negative and large field values."""
+    import ref_nav
+    lib = ref_nav.ref_lib()
+    if lib is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    ephs, iono = ref_nav.broadcast_ephemerides(lib)
+    assert len(ephs) > 300 and iono.vflg == 1
+    rng = np.random.default_rng(12)
+    for variant in range(3):
+        io = ref_nav.IonoUtc.from_buffer_copy(iono)
+        cases = list(ephs)
+        if variant == 1:
+            io.vflg = 0                                       # no ionosphere data: page 25 of subframe 4
+        if variant == 2:                                      # sign changes and other magnitudes in every scaled field
+            cases = []
+            for e in ephs[:120]:
+                p = ref_nav.Ephem.from_buffer_copy(e)
+                for n in ref_nav._EPH_D:
+                    setattr(p, n, getattr(p, n) * float(rng.choice([-1.0, 1.0])) * float(rng.uniform(0.2, 1.9)))
+                p.ecc, p.sqrta = abs(p.ecc), abs(p.sqrta)     # unsigned fields (a negative value is undefined in the reference)
+                p.iodc, p.iode = int(rng.integers(0, 1024)), int(rng.integers(0, 256))
+                cases.append(p)
+            for n in ("alpha0", "alpha1", "alpha2", "alpha3", "beta0", "beta1", "beta2", "beta3", "A0", "A1"):
+                setattr(io, n, -getattr(io, n) * 1.37)
+        want = np.stack([ref_nav.ref_subframes(lib, e, io) for e in cases])
+        got = emu_lib.eph2sbf(ref_nav.as_nav_eph(cases), ref_nav.as_nav_iono(io))
+        assert np.array_equal(got, want), variant
+
+
+def test_host_shim_names_the_right_ephemerides(tmp_path):
+    """GPUSIM_NAV_DEVICE=2 in dry-run mode on the satellite scenario: for every frame the shim registers, the subframes
+    the device algorithm makes of the ephemerides it names equal chan[i].sbf as the host's eph2sbf() left it (the frame
+    request of mode 1 carries a copy), and the words built from them equal chan[i].dwrd."""
+    host = os.path.join(ROOT, "integration", "_build", "gps-sdr-sim-gpu-int")
+    if not os.path.exists(host) or oracle_lib.ref_binary("int") is None:
+        pytest.skip("integration/_build or oracle/_ref not built (needs /root/reference)")
+    from gps_sdr_sim_b200 import NAV_EPH, NAV_IONO
+    dump = str(tmp_path / "nav2.bin")
+    env = dict(os.environ, GPUSIM_DRYRUN="1", GPUSIM_NAV_DEVICE="2", GPUSIM_NAV_DUMP=dump)
+    subprocess.run([host, "-e", oracle_lib.ref_data("brdc3540.14n"), "-u", oracle_lib.ref_data("satellite.csv"), "-i",
+                    "-s", "2600000", "-b", "16", "-o", "/dev/null"], env=env, check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+    rec = np.dtype([("frame", NAV_FRAME), ("dwrd", np.uint32, (60,)), ("eph", NAV_EPH), ("eph_first", NAV_EPH), ("iono", NAV_IONO)])
+    recs = np.fromfile(dump, dtype=rec)
+    assert recs.size >= 100
+    for r in recs:
+        sbf = emu_lib.eph2sbf(r["eph"].reshape(1), r["iono"])[0]
+        first = emu_lib.eph2sbf(r["eph_first"].reshape(1), r["iono"])[0][4]
+        assert np.array_equal(sbf, r["frame"]["sbf"]) and np.array_equal(first, r["frame"]["first"])
+        f = r["frame"].copy()
+        f["sbf"], f["first"] = sbf, first
+        assert np.array_equal(emu_lib.nav_build(f.reshape(1))[0], r["dwrd"])
